@@ -1,0 +1,480 @@
+#!/usr/bin/env python
+"""bench.py -- chain-iterations/s of the fused Hill log-target + adaptive-Metropolis path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (under torchrun for N > 1)
+    python bench.py --impl reference ...                      (CPU arm: the reference's algorithm on host cores)
+
+Workload (BASELINE.json configs[1]): every Crumb (drug, channel) pair (210) x single-level models {1, 2} x 64
+chains = 26 880 chains per GPU, PyHillFit-variant adaptive Metropolis (python/PyHillFit.py:828-856), thinning 5.
+One step = `--iters-per-step` iterations of every chain (two kernel launches, one per model, on two streams),
+thinned samples written to HBM.  N > 1: every rank runs the same workload with disjoint Philox chain ids (weak
+scaling, no collective on the data path); the value is chains x iterations over all ranks / max-over-ranks time.
+
+The JSON line carries: value (device-timed, inputs resident), e2e (through phf_am_single_run_host with pinned
+host buffers, H2D of state+data and D2H of samples+state inside the timed region), roofline (FP64: algorithmic
+flops W per chain-iteration from SURVEY.md section 8d / the live DFMA probe), cpu_baseline (the oracle's numpy/scipy
+restatement of the reference loop on all host cores, bounded sample), clocks, gpu_launches, ess_per_s.
+"""
+import argparse
+import json
+import math
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "chain-iterations/sec (all chains, device-timed)"
+UNIT = "chain-iterations/s"
+WORKLOAD = "Crumb: 210 drug-channel pairs x single-level models {1,2} x %d chains, PyHillFit AM, thinning %d"
+
+
+# ----------------------------------------------------------------------------------------------
+# algorithmic FP64 work per chain-iteration (SURVEY.md section 8d cost table; FMA = 2 flops)
+# ----------------------------------------------------------------------------------------------
+def flops_per_iteration(model, groups):
+    d = 2 if model == 1 else 3
+    D = len(groups)
+    d_other = int(np.count_nonzero(groups["n_other"] > 0))
+    d_cens = int(np.count_nonzero(groups["n0"] > 0) + np.count_nonzero(groups["n100"] > 0))
+    per_dose = 53 if model == 2 else 52
+    lik = 40 + 58 + D * per_dose + d_other * 5 + d_cens * 133 + 6
+    prior = 56
+    proposal = math.ceil(d / 2) * 118 + d * (d + 1) + d + 40
+    accept = 53
+    adapt = 3 * d * d + 16 * d + 4 * d + 3
+    return lik + prior + proposal + accept + adapt
+
+
+# ----------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------
+def build_workload(chains_per_pair):
+    from _data import Table
+    from pyhillfit_b200.initial_fit import best_fit
+    from pyhillfit_b200.packing import SinglePack
+    table = Table("crumb_data")
+    pairs = table.pairs()
+    data = [table.concat(d, c) for d, c in pairs]
+    pack = SinglePack(data)
+    rng = np.random.default_rng(25)
+    out = {}
+    for model in (1, 2):
+        d = 2 if model == 1 else 3
+        fits = np.stack([best_fit(model, *xy)[0] for xy in data])
+        theta0 = np.repeat(fits, chains_per_pair, axis=0)
+        jitter = 1.0 + 0.02 * rng.standard_normal(theta0.shape)
+        jitter[::chains_per_pair] = 1.0  # chain 0 of every pair starts exactly at the least-squares fit
+        theta0 = theta0 * jitter
+        theta0[:, -1] = np.maximum(theta0[:, -1], 2e-3)
+        if model == 2:
+            theta0[:, 1] = np.clip(theta0[:, 1], 1e-6, 10.0)
+        theta0[:, 0] = np.maximum(theta0[:, 0], -3.0)
+        ids = np.repeat(np.arange(len(pairs), dtype=np.int32), chains_per_pair)
+        w = np.array([flops_per_iteration(model, pack.groups[b:b + n]) for b, n in
+                      zip(pack.datasets["group_begin"], pack.datasets["n_groups"])], dtype=float)
+        out[model] = dict(theta0=theta0, ids=ids, d=d, flops=float(np.repeat(w, chains_per_pair).mean()))
+    return pack, out
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            if ts < t_begin or ts > t_end + 0.1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+                power.append(float(f[2]))
+            except Exception:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arms
+# ----------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One chain of the reference loop (numpy/scipy restatement, numpy RNG) -- returns seconds for `iters`."""
+    model, concs, y, theta0, warm, iters, seed = args
+    import numpy.random as npr
+    import hill_oracle as ho
+    w0, w100, wo = ho.masks(y)
+    pb = ho.compute_pi_bit_of_log_likelihood(wo)
+
+    def target(th):
+        return ho.log_target(model, y, w0, w100, wo, concs, th, 1, pb)
+
+    npr.seed(seed)
+    with np.errstate(all="ignore"):
+        ho.adaptive_metropolis(target, theta0, warm, 5, "fit", rng="numpy")
+        t0 = time.perf_counter()
+        ho.adaptive_metropolis(target, theta0, iters, 5, "fit", rng="numpy")
+        return time.perf_counter() - t0
+
+
+def cpu_reference_rate(iters, warm=500, cores=None):
+    """chain-iterations/s of the reference algorithm (oracle port) with one chain per host core."""
+    from _data import Table
+    from pyhillfit_b200.initial_fit import best_fit
+    cores = cores or mp.cpu_count()
+    table = Table("crumb_data")
+    concs, y = table.concat("Amiodarone", "hERG")
+    theta0, _ = best_fit(2, concs, y)
+    jobs = [(2, concs, y, theta0, warm, iters, 25 + k) for k in range(cores)]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        secs = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    return cores * iters / max(secs), cores, wall
+
+
+def cpu_c_port_rate(seconds=2.0):
+    """The C restatement (oracle/hill_oracle.c) on all cores: context for how much of the gap is Python."""
+    import c_oracle
+    import hill_oracle as ho
+    from _data import Table
+    table = Table("crumb_data")
+    concs, y = table.concat("Amiodarone", "hERG")
+    cores = mp.cpu_count()
+    n = cores * 4
+    pb = ho.compute_pi_bit_of_log_likelihood(y)
+    theta0 = np.array([6.0, 0.6, 7.7])
+    lt0, l10 = c_oracle.log_target_batch(2, concs, y, theta0[None], 1.0, pb)
+    st = np.tile(c_oracle.make_state(theta0, lt0[0], l10[0], 0.05 * np.diag(theta0)), (n, 1))
+    cls = c_oracle.classify(y)
+    iters = 20000
+    args = (n, np.full(n, 2, np.int32), np.full(n, len(y), np.int32), np.zeros(n, np.int64), concs, y, cls,
+            np.ones(n), np.full(n, pb), st, np.arange(n, dtype=np.int64) * st.shape[1], 0, iters, 5,
+            np.full(n, 3000, np.uint32), 0, 25, np.arange(n, dtype=np.uint64), cores)
+    t0 = time.perf_counter()
+    c_oracle.lib().phf_oracle_am_single_many(*args)
+    dt = time.perf_counter() - t0
+    return n * iters / dt, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    per_step = max(200, args.ref_iters_per_step)
+    rates = []
+    cores = mp.cpu_count()
+    for _ in range(args.warmup):
+        cpu_reference_rate(max(100, per_step // 10), warm=50)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, cores, _ = cpu_reference_rate(per_step, warm=100)
+        rates.append(r)
+    wall = time.perf_counter() - t0
+    value = float(np.mean(rates))
+    sample = ("%d chains (one per host core) x %d iterations per step of the PyHillFit single-level AM loop "
+              "(numpy/scipy restatement of python/PyHillFit.py:828-856 + doseresponse.py:187-248, numpy MT19937), "
+              "Amiodarone/hERG, model 2" % (cores, per_step))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD % (args.chains_per_pair, 5), "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--iters-per-step", type=int, default=10000)
+    ap.add_argument("--chains-per-pair", type=int, default=64)
+    ap.add_argument("--thinning", type=int, default=5)
+    ap.add_argument("--ref-iters-per-step", type=int, default=4000)
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--block-threads", type=int, default=0)
+    ap.add_argument("--no-stage", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from pyhillfit_b200 import _lib
+    from pyhillfit_b200.sampler import SingleLevelSampler
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    pack, wl = build_workload(args.chains_per_pair)
+    thin = args.thinning
+    K = args.iters_per_step
+    rows_per_step = K // thin
+    samplers, buffers, streams = {}, {}, {}
+    n_chains = 0
+    for model in (1, 2):
+        w = wl[model]
+        n = len(w["ids"])
+        # disjoint Philox streams per rank: global chain id = rank * n_total + local index
+        s = SingleLevelSampler(model, pack, w["ids"], 1.0, w["theta0"], variant="fit", seed=25,
+                               chain_id_base=(rank * 2 + (model - 1)) * (1 << 32), thinning=thin, device=dev,
+                               stage=not args.no_stage, block_threads=args.block_threads)
+        samplers[model] = s
+        buffers[model] = torch.empty((n, rows_per_step + 1, w["d"] + 1), dtype=torch.float64, device=dev)
+        streams[model] = torch.cuda.Stream(device=dev)
+        n_chains += n
+    flops_iter = sum(wl[m]["flops"] * len(wl[m]["ids"]) for m in (1, 2)) / n_chains
+    bytes_iter = sum((wl[m]["d"] + 1) * 8.0 / thin * len(wl[m]["ids"]) for m in (1, 2)) / n_chains
+
+    main_stream = torch.cuda.current_stream(dev)
+
+    def step():
+        ev = torch.cuda.Event()
+        ev.record(main_stream)
+        for model in (1, 2):
+            st = streams[model]
+            st.wait_event(ev)
+            with torch.cuda.stream(st):
+                samplers[model].run(K, samples=buffers[model])
+        for model in (1, 2):
+            main_stream.wait_stream(streams[model])
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin = time.time()
+    e0.record(main_stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(main_stream)
+    barrier()
+    t_end = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    clk = clocks.stop(t_begin, t_end) if rank == 0 else None
+    if world > 1:
+        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    total_iters = float(n_chains) * K * args.steps * world
+    value = total_iters / (ms * 1e-3)
+
+    # ---- per-kernel launch durations (each model's kernel alone on the device), for the roofline ----
+    kern_ms = {}
+    for model in (1, 2):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        a.record(main_stream)
+        samplers[model].run(K, samples=buffers[model])
+        b.record(main_stream)
+        torch.cuda.synchronize(dev)
+        kern_ms[model] = a.elapsed_time(b)
+
+    # ---- ESS/s from the last written step (512 chains sampled, min over parameters, Geyer IPS) ----
+    ess_per_s = None
+    acc = None
+    if rank == 0:
+        from pyhillfit_b200.ess import ess_min
+        rng = np.random.default_rng(0)
+        per_row = []
+        for model in (1, 2):
+            n = samplers[model].n
+            pick = rng.choice(n, size=min(256, n), replace=False)
+            smp = buffers[model][torch.as_tensor(pick, device=dev)][:, :rows_per_step, :wl[model]["d"]].cpu().numpy()
+            per_row.append(np.mean([ess_min(c) for c in smp]) / rows_per_step)
+        rows_per_s = value / thin
+        ess_per_s = float(np.mean(per_row) * rows_per_s)
+        acc = float(np.mean([samplers[m].acceptance().mean() for m in (1, 2)]))
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory) ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, torch, dev, pack, wl, samplers, rank, world, dist)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak_tf, _ = _lib.fp64_peak_tflops(5)
+    # dominant kernel = the model-2 sampler launch (am_single_kernel<2>)
+    n2 = samplers[2].n
+    ach_tf = n2 * K * wl[2]["flops"] / (kern_ms[2] * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                "traffic": None, "kernel": "am_single_kernel<2>", "launch_ms": kern_ms[2],
+                "flops_per_chain_iteration": wl[2]["flops"],
+                "peak_source": "phf_fp64_peak_probe (live DFMA microbenchmark; MEASURED_PEAKS.json has no FP64 entry)",
+                "hbm": {"achieved_gbs": n2 * K * (4 * 8.0 / thin) / (kern_ms[2] * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
+                        "algorithmic_bytes_per_chain_iteration": 4 * 8.0 / thin}}
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        r, cores, wall = cpu_reference_rate(6000, warm=300)
+        rc, _ = cpu_c_port_rate()
+        cpu_baseline = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "%d chains (one per host core) x 6000 iterations of the reference's single-level AM "
+                                  "loop, numpy/scipy restatement (oracle/hill_oracle.py), Amiodarone/hERG model 2; "
+                                  "%.1f s wall" % (cores, wall),
+                        "c_port_value": rc,
+                        "c_port_note": "same loop in plain C (oracle/hill_oracle.c, Philox RNG) on all cores"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD % (args.chains_per_pair, thin), "chains_per_gpu": n_chains,
+                       "iters_per_step": K, "theta0": "host least-squares fit; chains 1..63 of a pair jittered by 2%",
+                       "l2": "each step writes %.2f GB of thinned samples (> 126 MB L2); chain state is register-"
+                             "resident, packed data (54 KB) is staged in shared memory" %
+                             (sum(buffers[m][:, :rows_per_step].numel() for m in (1, 2)) * 8 / 1e9),
+                       "data_source": "Crumb et al. dose-response table (tests/golden/datasets.npz), random-start chains",
+                       "target_1e10_frac": value / world / 1e10},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clk, "ess_per_s": ess_per_s, "mean_acceptance": acc,
+            "hbm_bytes_per_chain_iteration": bytes_iter, "flops_per_chain_iteration": flops_iter,
+            "kernel_ms": {"am_single_kernel<1>": kern_ms[1], "am_single_kernel<2>": kern_ms[2]}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, torch, dev, pack, wl, samplers, rank, world, dist):
+    """Same step through phf_am_single_run_host: numpy/pinned host buffers in and out."""
+    import ctypes as C
+    from pyhillfit_b200 import _lib
+    L = _lib.load()
+    thin, K = args.thinning, args.iters_per_step
+    rows = K // thin
+    jobs = {}
+    h2d = d2h = 0
+    for model in (1, 2):
+        w = wl[model]
+        n, d = len(w["ids"]), w["d"]
+        st = torch.empty((n, _lib.state_size(d)), dtype=torch.float64).pin_memory()
+        st.copy_(samplers[model].state.cpu())
+        smp = torch.empty((n, rows, d + 1), dtype=torch.float64).pin_memory()
+        ids = np.ascontiguousarray(w["ids"])
+        temps = np.ones(n)
+        jobs[model] = dict(n=n, state=st, samples=smp, ids=ids, temps=temps, t0=samplers[model].t)
+        h2d += st.numel() * 8 + ids.nbytes + temps.nbytes + pack.datasets.nbytes + pack.groups.nbytes
+        d2h += smp.numel() * 8 + st.numel() * 8
+
+    def call(model):
+        j = jobs[model]
+        cfg = _lib.AmConfig(model=model, reset_mean_at_adapt=0, t0=j["t0"], n_iters=K, thinning=thin,
+                            adapt_when=1000 * wl[model]["d"], burn_rows=0xFFFFFFFF, rows_capacity=rows, seed=25,
+                            chain_id_base=(rank * 2 + (model - 1)) * (1 << 32), stage_groups=samplers[model].stage_groups,
+                            block_threads=samplers[model].block_threads)
+        rc = L.phf_am_single_run_host(C.byref(cfg), j["n"], j["state"].data_ptr(), j["ids"].ctypes.data,
+                                      j["temps"].ctypes.data, pack.n_datasets, pack.datasets.ctypes.data,
+                                      len(pack.groups), pack.groups.ctypes.data, j["samples"].data_ptr(), 8,
+                                      dev.index)
+        _lib.check(rc, "phf_am_single_run_host")
+        j["t0"] += K
+
+    def step():
+        th = [threading.Thread(target=call, args=(m,)) for m in (1, 2)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        step()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    total = float(sum(j["n"] for j in jobs.values())) * K * args.e2e_steps * world
+    return {"value": total / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "steps": args.e2e_steps, "api": "phf_am_single_run_host (pinned host buffers, 8 overlapped segments/call)",
+            "timing": "host wall clock around synchronous calls (each call ends with a stream synchronise)"}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

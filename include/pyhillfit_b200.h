@@ -1,0 +1,183 @@
+/*
+ * pyhillfit_b200 -- C ABI of the B200 (sm_100a) implementation of PyHillFit's MCMC hot path.
+ *
+ * The reference (mirams/PyHillFit) has no FFI: its seam is Python-function level.  Each entry point
+ * below names the reference function(s) it replaces (paths relative to the reference root); the ctypes
+ * stub a maintainer would add on the reference side is in INTEGRATION.md, and the repo's own host side
+ * (pyhillfit_b200/_lib.py, doseresponse.py, sampler.py) is exactly that stub.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  Unless a name ends in _host, every pointer is a DEVICE
+ *     pointer owned by the caller (e.g. a torch tensor's data_ptr()); the library allocates nothing
+ *     persistent for those calls and is asynchronous on `stream` (a cudaStream_t passed as void*; NULL =
+ *     the legacy default stream).
+ *   - return value: 0 on success, a negative PHF_E* code otherwise; phf_last_error() gives the text.
+ *     Nothing throws; there is no CPU fallback.
+ *   - all arithmetic is IEEE fp64 (no fast-math).  Out-of-support parameters give -inf exactly where the
+ *     reference does; finite inputs never give NaN.
+ */
+#ifndef PYHILLFIT_B200_H
+#define PYHILLFIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHF_VERSION 100 /* 0.1.0 */
+
+#define PHF_OK 0
+#define PHF_EINVAL (-1)   /* bad argument */
+#define PHF_ECUDA (-2)    /* CUDA runtime error (see phf_last_error) */
+#define PHF_ENOTSUP (-3)  /* configuration outside what the kernels cover (e.g. too many experiments) */
+
+/* ------------------------------------------------------------------------------------------------
+ * Packed single-level data (built host-side by pyhillfit_b200/packing.py).
+ *
+ * The reference keeps, per (drug, channel), flat arrays concs[N], responses[N] and three boolean masks
+ * (python/PyHillFit.py:661-677, python/PyHillTemp.py:132-140).  Replicates of one dose share the Hill
+ * curve value, so the likelihood of python/doseresponse.py:203-248 collapses to one term per UNIQUE dose:
+ *   sum_{y other} (y-p)^2 = ss + n_other (ybar-p)^2,   n0 * logPhi((0-p)/sigma),   n100 * logPhi((p-100)/sigma)
+ * A response outside [0,100] is in no mask and contributes nothing except to pi_bit (N_total).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct phf_dose_group { /* 64 bytes */
+    double lnc_hi;   /* ln(dose), rounded to double; -inf for dose 0 */
+    double lnc_lo;   /* ln(dose) - lnc_hi (double-double tail), 0 if lnc_hi is not finite */
+    double conc;     /* dose itself (model 1 uses dose / IC50 directly) */
+    double n_other;  /* # responses with 0 < y < 100 at this dose */
+    double ybar;     /* their mean (0 if none) */
+    double ss;       /* their centred sum of squares sum (y - ybar)^2 */
+    double n0;       /* # responses == 0   (left-censored,  python/doseresponse.py:218,244) */
+    double n100;     /* # responses == 100 (right-censored, python/doseresponse.py:219,245) */
+} phf_dose_group;
+
+typedef struct phf_dataset { /* 32 bytes */
+    int32_t group_begin;   /* first phf_dose_group of this dataset */
+    int32_t n_groups;      /* number of unique doses */
+    double pi_bit;         /* 0.5 * N_total * ln(2 pi): python/doseresponse.py:299-301 as called at PyHillFit.py:683 */
+    double n_other_total;  /* where_y_other.sum(): python/doseresponse.py:220,246 */
+    double reserved;
+} phf_dataset;
+
+/*
+ * Batched log-target.  Replaces dr.log_target / dr.log_data_likelihood / dr.log_priors
+ * (python/doseresponse.py:166-189, 203-248) for n parameter vectors at once.
+ *   model        1: params (pIC50, sigma), Hill fixed at 1;  2: params (pIC50, Hill, sigma)
+ *   theta        [n, d] row-major, d = 2 or 3
+ *   dataset_id   [n]    index into `datasets`
+ *   temperature  [n]    power-posterior temperature t (likelihood is multiplied by t; t == 0 -> prior only)
+ *   log_target   [n]    out: t * loglik + logprior
+ *   loglik_t1    [n]    out, may be NULL: the temperature-1 log-likelihood of the same theta
+ *                       (what python/compute_bayes_factors.py:18-21 re-evaluates row by row)
+ */
+int phf_log_target_batch(int model, int64_t n, const double *theta, const int32_t *dataset_id,
+                         const double *temperature, const phf_dataset *datasets, const phf_dose_group *groups,
+                         double *log_target, double *loglik_t1, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused adaptive-Metropolis, single-level models.  Replaces the loops at python/PyHillFit.py:828-856
+ * (variant "fit") and python/PyHillTemp.py:87-123 (variant "temp") for n_chains independent chains, K
+ * iterations per launch, chain state resident in registers, data staged in shared memory.
+ *
+ * Chain state, one row of `state` per chain, PHF_STATE_SIZE(d) doubles:
+ *   theta[d], log_target, loglik_t1, mean[d], cov[d(d+1)/2] (lower triangle, row-major), loga,
+ *   loglik_t1_sum (over saved rows with index >= burn_rows), n_accepted
+ * RNG: Philox4x32-10, key = seed, counter = (iteration, call, chain_id lo, chain_id hi); the stream
+ * contract is written out in oracle/hill_oracle.py (the oracle reproduces GPU trajectories with it).
+ * ---------------------------------------------------------------------------------------------- */
+#define PHF_STATE_SIZE(d) (2 * (d) + (d) * ((d) + 1) / 2 + 5)
+
+typedef struct phf_am_config {
+    int32_t model;               /* 1 or 2 (ignored by the hierarchical entry points) */
+    int32_t reset_mean_at_adapt; /* 1: mean <- theta at t == adapt_when (python/PyHillTemp.py:114-115) */
+    uint32_t t0;                 /* iterations already done; this call runs t0+1 .. t0+n_iters */
+    uint32_t n_iters;
+    uint32_t thinning;           /* row t/thinning is saved when t % thinning == 0 */
+    uint32_t adapt_when;         /* adaptation for t > adapt_when: 1000*d (fit, temp) or 100*d (hier) */
+    uint32_t burn_rows;          /* saved rows with index >= burn_rows add loglik_t1 to loglik_t1_sum */
+    uint32_t rows_capacity;      /* rows per chain in `samples` (>= rows this call produces) */
+    uint64_t seed;
+    uint64_t chain_id_base;      /* global id of local chain 0 (ranks shard one global chain list) */
+    int32_t stage_groups;        /* shared-memory staging capacity per CTA in dose groups / points (0: read via L1) */
+    int32_t block_threads;       /* 0: library default */
+} phf_am_config;
+
+/* Evaluate the target at theta0 and fill `state` (mean = theta0, cov = cov0, loga = 0, counters = 0). */
+int phf_am_single_init(int model, int64_t n_chains, const double *theta0 /* [n,d] */,
+                       const double *cov0_tri /* [n, d(d+1)/2] */, const int32_t *dataset_id,
+                       const double *temperature, const phf_dataset *datasets, const phf_dose_group *groups,
+                       double *state /* [n, PHF_STATE_SIZE(d)] */, void *stream);
+
+/*
+ * Run cfg->n_iters iterations of every chain.  `samples` ([n_chains, rows_capacity, d+1], may be NULL)
+ * receives (theta, log_target) for each saved row of this call: local row = t/thinning - t0/thinning - 1.
+ * Chains must be sorted by dataset_id when cfg->stage_groups > 0.
+ */
+int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, double *state, const int32_t *dataset_id,
+                      const double *temperature, const phf_dataset *datasets, const phf_dose_group *groups,
+                      double *samples, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Hierarchical model (python/PyHillFit.py:113-154, 173-193, 481-511).
+ * theta = (alpha, beta, mu, s, pIC50_1, Hill_1, ..., pIC50_Ne, Hill_Ne, sigma), dim = 5 + 2 Ne.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct phf_hier_point { /* 32 bytes */
+    double lnc_hi, lnc_lo; /* as in phf_dose_group */
+    double y;              /* response */
+    int32_t expt;          /* 0-based experiment index within the dataset */
+    int32_t pad;
+} phf_hier_point;
+
+typedef struct phf_hier_dataset { /* 16 bytes */
+    int32_t point_begin, n_points, n_expts, pad;
+} phf_hier_dataset;
+
+typedef struct phf_hier_priors {
+    double shapes[5], scales[5], locs[5]; /* Gamma hyper-priors on (alpha, beta, mu, s, sigma): PyHillFit.py:301,340-364 */
+    double pic50_lower;                   /* -2: PyHillFit.py:215 */
+} phf_hier_priors;
+
+#define PHF_HIER_MAX_EXPTS 13 /* dim <= 31: one warp lane per parameter row */
+
+/* theta rows have stride `theta_stride` doubles (>= dim of the row's dataset). */
+int phf_hier_log_target_batch(int64_t n, const double *theta, int32_t theta_stride, const int32_t *dataset_id,
+                              const phf_hier_dataset *datasets, const phf_hier_point *points,
+                              const phf_hier_priors *priors /* HOST pointer */, double *log_target, void *stream);
+
+/* All chains of one call share n_expts (so dim); state rows are PHF_STATE_SIZE(dim) doubles. */
+int phf_am_hier_init(int32_t n_expts, int64_t n_chains, const double *theta0 /* [n,dim] */,
+                     const double *cov0_tri /* [n, dim(dim+1)/2] */, const int32_t *dataset_id,
+                     const phf_hier_dataset *datasets, const phf_hier_point *points,
+                     const phf_hier_priors *priors /* HOST */, double *state, void *stream);
+
+int phf_am_hier_run(const phf_am_config *cfg, int32_t n_expts, int64_t n_chains, double *state,
+                    const int32_t *dataset_id, const phf_hier_dataset *datasets, const phf_hier_point *points,
+                    const phf_hier_priors *priors /* HOST */, double *samples /* [n, rows_capacity, dim+1] */,
+                    void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer entry point (the reference-facing call: numpy arrays in, numpy arrays out).
+ * Every pointer is a HOST pointer (pinned memory makes the copies asynchronous).  One call = copy state
+ * and data to the device, run cfg->n_iters iterations in `n_segments` launches whose sample write-back
+ * overlaps the next launch, copy state and samples back, synchronise.  `device` selects the GPU.
+ * ---------------------------------------------------------------------------------------------- */
+int phf_am_single_run_host(const phf_am_config *cfg, int64_t n_chains, double *state, const int32_t *dataset_id,
+                           const double *temperature, int32_t n_datasets, const phf_dataset *datasets,
+                           int32_t n_groups, const phf_dose_group *groups, double *samples, int32_t n_segments,
+                           int32_t device);
+
+/* ------------------------------------------------------------------------------------------------
+ * Utilities
+ * ---------------------------------------------------------------------------------------------- */
+int phf_version(void);
+const char *phf_last_error(void);
+/* dependent-free DFMA microbenchmark on the current device: the FP64 roofline denominator (TFLOP/s) */
+int phf_fp64_peak_probe(int32_t repeats, double *tflops_out, double *seconds_out);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t phf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYHILLFIT_B200_H */

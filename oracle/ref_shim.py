@@ -59,8 +59,9 @@ def _extract_functions(path, names, int_div=False):
             def visit_BinOp(self, node):
                 self.generic_visit(node)
                 if isinstance(node.op, ast.Div):
-                    txt = ast.unparse(node)
-                    if "." not in txt:
+                    has_float = any(isinstance(c, ast.Constant) and isinstance(c.value, float)
+                                    for c in ast.walk(node))
+                    if not has_float:
                         node.op = ast.FloorDiv()
                 return node
         keep = [_FloorDiv().visit(k) for k in keep]

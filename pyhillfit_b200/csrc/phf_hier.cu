@@ -1,0 +1,423 @@
+// Hierarchical model: log-target (python/PyHillFit.py:113-154, 173-193) and the fused adaptive-Metropolis
+// sampler (python/PyHillFit.py:481-511).  One group of G lanes (G = 16 or 32) owns one chain:
+//   lane j holds theta_j, mean_j, row j of the proposal covariance and of its Cholesky factor in registers;
+//   lane i evaluates data point i (Hill curve, truncated-normal normaliser);
+//   lanes 4..dim-2 evaluate the per-experiment logistic / log-logistic terms;
+//   sums are fp64 xor-shuffle reductions inside the group.
+#include "phf_common.cuh"
+#include "phf_math.cuh"
+
+namespace phf {
+
+template <int G>
+PHF_DI unsigned group_mask()
+{
+    return G == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16u));
+}
+
+template <int G>
+PHF_DI double group_sum(double v, unsigned mask)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
+    return v;
+}
+
+// Per-lane constants of the Gamma hyper-priors on theta[[0,1,2,3,-1]] (PyHillFit.py:187, 301, 363-364).
+struct LanePrior {
+    double loc, shape_m1, inv_scale;  // zero on lanes that carry no hyper-prior
+    double lower;                     // support: theta_j < lower (or <= for strict) is outside
+    bool strict;                      // true: theta_j <= lower is outside (PyHillFit.py:176,182)
+    bool has_gamma;
+};
+
+PHF_DI LanePrior lane_prior(int gl, int dim, const phf_hier_priors &pr)
+{
+    LanePrior lp;
+    lp.loc = 0.0; lp.shape_m1 = 0.0; lp.inv_scale = 0.0; lp.lower = -CUDART_INF; lp.strict = false;
+    lp.has_gamma = false;
+    int slot = -1;
+    if (gl < 4) slot = gl;
+    if (gl == dim - 1) slot = 4;
+    if (slot >= 0) {
+        // compile-time indices only (kernel parameters live in the constant bank)
+        const double loc = slot == 0 ? pr.locs[0] : slot == 1 ? pr.locs[1] : slot == 2 ? pr.locs[2]
+                         : slot == 3 ? pr.locs[3] : pr.locs[4];
+        const double shp = slot == 0 ? pr.shapes[0] : slot == 1 ? pr.shapes[1] : slot == 2 ? pr.shapes[2]
+                         : slot == 3 ? pr.shapes[3] : pr.shapes[4];
+        const double scl = slot == 0 ? pr.scales[0] : slot == 1 ? pr.scales[1] : slot == 2 ? pr.scales[2]
+                         : slot == 3 ? pr.scales[3] : pr.scales[4];
+        lp.loc = loc; lp.shape_m1 = shp - 1.0; lp.inv_scale = 1.0 / scl; lp.lower = loc; lp.strict = true;
+        lp.has_gamma = true;
+    } else if (gl < dim - 1) {
+        // gl = 4+2e: pIC50_e >= pic50_lower; gl = 5+2e: Hill_e >= 0 (PyHillFit.py:182)
+        lp.lower = (gl & 1) ? 0.0 : pr.pic50_lower;
+    }
+    return lp;
+}
+
+struct HierPoint {
+    double lnc_hi, lnc_lo, y;
+    int expt;
+};
+
+PHF_DI HierPoint load_point(const phf_hier_point *p)
+{
+    HierPoint h;
+    const double4 v = *reinterpret_cast<const double4 *>(p);
+    h.lnc_hi = v.x; h.lnc_lo = v.y; h.y = v.z;
+    h.expt = (int)(__double_as_longlong(v.w) & 0xffffffffll);
+    return h;
+}
+
+// log_target_distribution for the theta whose entry j sits on lane j of the group.  All lanes of the group
+// must call it; the result is uniform across the group.
+template <int G>
+PHF_DI double hier_log_target(double th_j, int gl, int dim, const LanePrior &lp, const HierPoint &pt0,
+                              const phf_hier_point *__restrict__ pts, int npts, unsigned mask)
+{
+    // ---- support (PyHillFit.py:176-183) ----
+    bool bad = false;
+    if (gl < dim) bad = lp.strict ? !(th_j > lp.lower) : !(th_j >= lp.lower);
+    bad = __any_sync(mask, bad) != 0;
+
+    // ---- one vector log for every entry, one for the Gamma hyper-priors ----
+    const double lth = log(th_j);
+    const double xm = th_j - lp.loc;
+    double term = 0.0;
+    {
+        const double lg = log(xm);
+        if (lp.has_gamma) term = fma(lp.shape_m1, lg, -xm * lp.inv_scale);  // dr.log_gamma_prior (doseresponse.py:308)
+    }
+    const double alpha_l = __shfl_sync(mask, lth, 0, G);
+    const double beta = __shfl_sync(mask, th_j, 1, G);
+    const double beta_l = __shfl_sync(mask, lth, 1, G);
+    const double mu = __shfl_sync(mask, th_j, 2, G);
+    const double s = __shfl_sync(mask, th_j, 3, G);
+    const double s_l = __shfl_sync(mask, lth, 3, G);
+    const double sigma = __shfl_sync(mask, th_j, dim - 1, G);
+    const double sigma_l = __shfl_sync(mask, lth, dim - 1, G);
+
+    // ---- per-experiment terms: logistic on pIC50_e (even lane), log-logistic on Hill_e (odd lane) ----
+    {
+        const bool is_pic50 = (gl & 1) == 0;
+        const double zz = (th_j - mu) / s;                                   // PyHillFit.py:145
+        const double arg = is_pic50 ? -zz : beta * (lth - alpha_l);          // (x/alpha)**beta, PyHillFit.py:135
+        const double v = exp(arg);
+        const double l = log(1.0 + v);
+        const double t_pic = -zz - s_l - 2.0 * l;                            // PyHillFit.py:146
+        const double t_hill = beta_l - beta * alpha_l + (beta - 1.0) * lth - 2.0 * l;  // PyHillFit.py:135
+        if (gl >= 4 && gl < dim - 1) term = is_pic50 ? t_pic : t_hill;
+    }
+
+    // ---- data likelihood, truncated-normal noise (PyHillFit.py:113-125): one point per lane per round ----
+    const double inv_s = 1.0 / sigma;
+    const double inv2s2 = 0.5 * inv_s * inv_s;
+    for (int base = 0; base < npts; base += G) {
+        const int pi = base + gl;
+        const bool has = pi < npts;
+        HierPoint P = pt0;
+        if (base > 0) P = load_point(pts + (has ? pi : 0));
+        const int e = has ? P.expt : 0;
+        const double pic50_e = __shfl_sync(mask, th_j, 4 + 2 * e, G);
+        const double hill_e = __shfl_sync(mask, th_j, 5 + 2 * e, G);
+        double lic_hi, lic_lo;
+        ln_ic50(pic50_e, lic_hi, lic_lo);
+        const double x = hill_ratio_pow(P.lnc_hi, P.lnc_lo, lic_hi, lic_lo, hill_e);
+        const double p = hill_response(x);
+        const double r = P.y - p;
+        // st.norm.cdf(100,p,sigma) - st.norm.cdf(0,p,sigma) with Phi(a) = erfc(-a/sqrt2)/2
+        const double a = (100.0 - p) * inv_s, b = (0.0 - p) * inv_s;
+        const double dphi = 0.5 * (erfc(-a * kSqrtHalf) - erfc(-b * kSqrtHalf));
+        const double contrib = -(fma(r * r, inv2s2, log(dphi)) + sigma_l);
+        if (has) term += contrib;
+    }
+    const double total = group_sum<G>(term, mask);
+    return bad ? -CUDART_INF : total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched log-target: one 32-lane group per parameter vector, runtime dim <= 31
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) hier_log_target_batch_kernel(int64_t n, const double *__restrict__ theta,
+                                                                    int32_t theta_stride,
+                                                                    const int32_t *__restrict__ dataset_id,
+                                                                    const phf_hier_dataset *__restrict__ datasets,
+                                                                    const phf_hier_point *__restrict__ points,
+                                                                    phf_hier_priors pr, double *__restrict__ out)
+{
+    constexpr int G = 32;
+    const int gl = threadIdx.x & (G - 1);
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (i >= n) return;  // whole warp exits together
+    const phf_hier_dataset ds = datasets[dataset_id[i]];
+    const int dim = 5 + 2 * ds.n_expts;
+    const double th_j = gl < dim ? theta[i * theta_stride + gl] : 1.0;
+    const LanePrior lp = lane_prior(gl, dim, pr);
+    const phf_hier_point *pts = points + ds.point_begin;
+    const HierPoint pt0 = load_point(pts + (gl < ds.n_points ? gl : 0));
+    const double lt = hier_log_target<G>(th_j, gl, dim, lp, pt0, pts, ds.n_points, 0xffffffffu);
+    if (gl == 0) out[i] = lt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// state init
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) am_hier_init_kernel(int32_t dim, int64_t n, const double *__restrict__ theta0,
+                                                           const double *__restrict__ cov0,
+                                                           const int32_t *__restrict__ dataset_id,
+                                                           const phf_hier_dataset *__restrict__ datasets,
+                                                           const phf_hier_point *__restrict__ points,
+                                                           phf_hier_priors pr, double *__restrict__ state)
+{
+    constexpr int G = 32;
+    const int gl = threadIdx.x & (G - 1);
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (i >= n) return;
+    const phf_hier_dataset ds = datasets[dataset_id[i]];
+    const int nt = dim * (dim + 1) / 2, nf = PHF_STATE_SIZE(dim);
+    const double th_j = gl < dim ? theta0[i * dim + gl] : 1.0;
+    const LanePrior lp = lane_prior(gl, dim, pr);
+    const phf_hier_point *pts = points + ds.point_begin;
+    const HierPoint pt0 = load_point(pts + (gl < ds.n_points ? gl : 0));
+    const double lt = hier_log_target<G>(th_j, gl, dim, lp, pt0, pts, ds.n_points, 0xffffffffu);
+    double *s = state + i * nf;
+    if (gl < dim) {
+        s[gl] = th_j;
+        s[dim + 2 + gl] = th_j;
+    }
+    for (int k = gl; k < nt; k += G) s[2 * dim + 2 + k] = cov0[i * nt + k];
+    if (gl == 0) {
+        s[dim] = lt;
+        s[dim + 1] = 0.0;
+        s[2 * dim + 2 + nt] = 0.0;
+        s[2 * dim + 2 + nt + 1] = 0.0;
+        s[2 * dim + 2 + nt + 2] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused adaptive Metropolis, hierarchical (PyHillFit.py:481-511)
+// ------------------------------------------------------------------------------------------------
+template <int G, int DIM>
+__global__ void __launch_bounds__(128) am_hier_kernel(phf_am_config cfg, int64_t n, double *__restrict__ state,
+                                                      const int32_t *__restrict__ dataset_id,
+                                                      const phf_hier_dataset *__restrict__ datasets,
+                                                      const phf_hier_point *__restrict__ points, phf_hier_priors pr,
+                                                      double *__restrict__ samples)
+{
+    static_assert(DIM < G, "one lane per parameter row plus one for the log-target column");
+    constexpr int NT = DIM * (DIM + 1) / 2, NF = PHF_STATE_SIZE(DIM);
+    const int gl = threadIdx.x & (G - 1);
+    const unsigned lane = threadIdx.x & 31u;
+    const int64_t chain = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool active = chain < n;
+    const int64_t c = active ? chain : n - 1;
+    const unsigned mask = group_mask<G>();
+
+    const phf_hier_dataset ds = datasets[dataset_id[c]];
+    const phf_hier_point *pts = points + ds.point_begin;
+    const int npts = ds.n_points;
+    const HierPoint pt0 = load_point(pts + (gl < npts ? gl : 0));
+    const LanePrior lp = lane_prior(gl, DIM, pr);
+    const uint64_t chain_id = cfg.chain_id_base + (uint64_t)c;
+
+    // ---- state: lane j holds theta_j, mean_j and row j of the covariance ----
+    double *sp = state + c * NF;
+    const bool row_ok = gl < DIM;
+    double th_j = row_ok ? sp[gl] : 1.0;
+    double mean_j = row_ok ? sp[DIM + 2 + gl] : 1.0;
+    double lt = sp[DIM];
+    double crow[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) crow[k] = (row_ok && k <= gl) ? sp[2 * DIM + 2 + gl * (gl + 1) / 2 + k] : 0.0;
+    double loga = sp[2 * DIM + 2 + NT];
+    double n_acc = sp[2 * DIM + 2 + NT + 2];
+
+    // ---- this lane's slice of the Philox stream: normal pair q = j/2 (contract: oracle/hill_oracle.py) ----
+    const uint32_t q = (uint32_t)gl >> 1;
+    const uint32_t call = q == 0u ? 0u : (q + 1u) >> 1;
+    const bool hi_words = (q == 0u) || ((q & 1u) == 0u);  // words 2,3
+
+    uint32_t t = cfg.t0;
+    uint32_t until_save = cfg.thinning - (t % cfg.thinning);
+    uint32_t row = t / cfg.thinning;
+    const uint32_t row_base = row + 1;
+    double *out = samples ? samples + (size_t)c * cfg.rows_capacity * (DIM + 1) : nullptr;
+    double gam_lane = 0.0;
+
+    for (uint32_t it = 0; it < cfg.n_iters; ++it) {
+        ++t;
+        if ((it & 31u) == 0u) {
+            const uint32_t tl = t + lane;
+            gam_lane = tl > cfg.adapt_when ? 1.0 / pow((double)(tl - cfg.adapt_when) + 1.0, 0.6) : 0.0;  // PyHillFit.py:496-497
+        }
+        const double gam = __shfl_sync(0xffffffffu, gam_lane, it & 31u);
+
+        // ---- draws ----
+        double z_j, u;
+        {
+            const Philox4 r = philox_call(cfg.seed, chain_id, t, call);
+            double z0, z1;
+            box_muller(hi_words ? r.w[2] : r.w[0], hi_words ? r.w[3] : r.w[1], z0, z1);
+            z_j = (gl & 1) ? z1 : z0;
+            u = __shfl_sync(mask, uniform53(r.w[0], r.w[1]), 0, G);  // lane 0 made call 0
+        }
+
+        // ---- Cholesky factor of the covariance, left-looking, row j on lane j ----
+        double lrow[DIM];
+#pragma unroll
+        for (int col = 0; col < DIM; ++col) {
+            double v = crow[col];
+#pragma unroll
+            for (int k = 0; k < col; ++k) v = fma(-lrow[k], __shfl_sync(mask, lrow[k], col, G), v);
+            const double piv = __shfl_sync(mask, v, col, G);
+            const double rinv = rsqrt(piv);
+            lrow[col] = gl >= col ? v * rinv : 0.0;
+        }
+
+        // ---- proposal theta* = theta + e^{loga/2} L z  (N(theta, e^loga cov): PyHillFit.py:485) ----
+        double star_j;
+        {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) acc = fma(lrow[k], __shfl_sync(mask, z_j, k, G), acc);
+            star_j = fma(exp(0.5 * loga), acc, th_j);
+        }
+
+        // ---- target, accept (PyHillFit.py:486-493) ----
+        const double lt_star = hier_log_target<G>(star_j, gl, DIM, lp, pt0, pts, npts, mask);
+        const bool accepted = log(u) < lt_star - lt;
+        if (accepted) {
+            th_j = star_j;
+            lt = lt_star;
+            n_acc += 1.0;
+        }
+
+        // ---- adaptation (PyHillFit.py:495-501) ----
+        if (t > cfg.adapt_when) {
+            const double omg = 1.0 - gam;
+            const double dv_j = th_j - mean_j;
+            const double gd = gam * dv_j;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) crow[k] = fma(gd, __shfl_sync(mask, dv_j, k, G), omg * crow[k]);
+            mean_j = fma(gam, th_j, omg * mean_j);
+            loga = fma(gam, (accepted ? 1.0 : 0.0) - 0.25, loga);
+        }
+
+        // ---- thinned write-out (PyHillFit.py:502-503): lanes write one row, coalesced ----
+        if (--until_save == 0u) {
+            until_save = cfg.thinning;
+            ++row;
+            if (out && active) {
+                double *o = out + (size_t)(row - row_base) * (DIM + 1);
+                if (row_ok) o[gl] = th_j;
+                if (gl == DIM) o[DIM] = lt;
+            }
+        }
+    }
+
+    if (active) {
+        if (row_ok) {
+            sp[gl] = th_j;
+            sp[DIM + 2 + gl] = mean_j;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k)
+                if (k <= gl) sp[2 * DIM + 2 + gl * (gl + 1) / 2 + k] = crow[k];
+        }
+        if (gl == 0) {
+            sp[DIM] = lt;
+            sp[2 * DIM + 2 + NT] = loga;
+            sp[2 * DIM + 2 + NT + 2] = n_acc;
+        }
+    }
+}
+
+template <int G, int DIM>
+static int launch_am_hier(const phf_am_config &cfg, int64_t n, double *state, const int32_t *dataset_id,
+                          const phf_hier_dataset *datasets, const phf_hier_point *points, const phf_hier_priors &pr,
+                          double *samples, cudaStream_t s)
+{
+    const int block = 128;  // 4 warps; G lanes per chain
+    const int64_t lanes = n * G;
+    const unsigned grid = (unsigned)((lanes + block - 1) / block);
+    am_hier_kernel<G, DIM><<<grid, block, 0, s>>>(cfg, n, state, dataset_id, datasets, points, pr, samples);
+    count_launch();
+    return check_launch("am_hier_kernel");
+}
+
+}  // namespace phf
+
+using namespace phf;
+
+extern "C" int phf_hier_log_target_batch(int64_t n, const double *theta, int32_t theta_stride,
+                                         const int32_t *dataset_id, const phf_hier_dataset *datasets,
+                                         const phf_hier_point *points, const phf_hier_priors *priors,
+                                         double *log_target, void *stream)
+{
+    if (n < 0 || !priors || (n > 0 && (!theta || !dataset_id || !datasets || !points || !log_target)))
+        return set_error(PHF_EINVAL, "phf_hier_log_target_batch: null pointer");
+    if (theta_stride < 7) return set_error(PHF_EINVAL, "theta_stride < 7");
+    if (n == 0) return PHF_OK;
+    const int block = 128;
+    const unsigned grid = (unsigned)((n * 32 + block - 1) / block);
+    hier_log_target_batch_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n, theta, theta_stride, dataset_id,
+                                                                           datasets, points, *priors, log_target);
+    count_launch();
+    return check_launch("hier_log_target_batch_kernel");
+}
+
+extern "C" int phf_am_hier_init(int32_t n_expts, int64_t n_chains, const double *theta0, const double *cov0_tri,
+                                const int32_t *dataset_id, const phf_hier_dataset *datasets,
+                                const phf_hier_point *points, const phf_hier_priors *priors, double *state,
+                                void *stream)
+{
+    if (n_expts < 1 || n_expts > PHF_HIER_MAX_EXPTS) return set_error(PHF_ENOTSUP, "n_expts outside 1..13");
+    if (n_chains < 0 || !priors ||
+        (n_chains > 0 && (!theta0 || !cov0_tri || !dataset_id || !datasets || !points || !state)))
+        return set_error(PHF_EINVAL, "phf_am_hier_init: null pointer");
+    if (n_chains == 0) return PHF_OK;
+    const int block = 128;
+    const unsigned grid = (unsigned)((n_chains * 32 + block - 1) / block);
+    am_hier_init_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(5 + 2 * n_expts, n_chains, theta0, cov0_tri,
+                                                                  dataset_id, datasets, points, *priors, state);
+    count_launch();
+    return check_launch("am_hier_init_kernel");
+}
+
+extern "C" int phf_am_hier_run(const phf_am_config *cfg, int32_t n_expts, int64_t n_chains, double *state,
+                               const int32_t *dataset_id, const phf_hier_dataset *datasets,
+                               const phf_hier_point *points, const phf_hier_priors *priors, double *samples,
+                               void *stream)
+{
+    if (!cfg || !priors) return set_error(PHF_EINVAL, "phf_am_hier_run: cfg/priors is NULL");
+    if (n_expts < 1 || n_expts > PHF_HIER_MAX_EXPTS) return set_error(PHF_ENOTSUP, "n_expts outside 1..13");
+    if (cfg->thinning == 0) return set_error(PHF_EINVAL, "cfg.thinning must be >= 1");
+    if (n_chains < 0 || (n_chains > 0 && (!state || !dataset_id || !datasets || !points)))
+        return set_error(PHF_EINVAL, "phf_am_hier_run: null pointer");
+    if ((uint64_t)cfg->t0 + cfg->n_iters > 0xFFFFFFFFull) return set_error(PHF_EINVAL, "iteration counter overflow");
+    const uint32_t rows = (cfg->t0 + cfg->n_iters) / cfg->thinning - cfg->t0 / cfg->thinning;
+    if (samples && rows > cfg->rows_capacity)
+        return set_error(PHF_EINVAL, "cfg.rows_capacity is smaller than the rows this call produces");
+    if (n_chains == 0 || cfg->n_iters == 0) return PHF_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+#define PHF_HIER_CASE(NE, G) \
+    case NE: return launch_am_hier<G, 5 + 2 * NE>(*cfg, n_chains, state, dataset_id, datasets, points, *priors, samples, s)
+    switch (n_expts) {
+        PHF_HIER_CASE(1, 16);
+        PHF_HIER_CASE(2, 16);
+        PHF_HIER_CASE(3, 16);
+        PHF_HIER_CASE(4, 16);
+        PHF_HIER_CASE(5, 16);
+        PHF_HIER_CASE(6, 32);
+        PHF_HIER_CASE(7, 32);
+        PHF_HIER_CASE(8, 32);
+        PHF_HIER_CASE(9, 32);
+        PHF_HIER_CASE(10, 32);
+        PHF_HIER_CASE(11, 32);
+        PHF_HIER_CASE(12, 32);
+        PHF_HIER_CASE(13, 32);
+    }
+#undef PHF_HIER_CASE
+    return set_error(PHF_ENOTSUP, "n_expts outside 1..13");
+}

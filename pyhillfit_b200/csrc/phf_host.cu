@@ -1,0 +1,129 @@
+// Host-buffer entry point: the call a numpy-level user of the reference would make.  Copies in, runs the
+// fused sampler in segments whose sample write-back (D2H) overlaps the next segment's kernel, copies out.
+#include <algorithm>
+#include <vector>
+
+#include "phf_common.cuh"
+
+using namespace phf;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+};
+
+// Per-device workspace reused across calls (a sampler is called once per segment of a long run).
+struct Workspace {
+    DevBuf state, dsid, temp, datasets, groups, samples[2];
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    bool init = false;
+};
+
+Workspace g_ws[16][2];  // [device][model-1]: the two models may be driven from two host threads
+
+}  // namespace
+
+extern "C" int phf_am_single_run_host(const phf_am_config *cfg, int64_t n_chains, double *state,
+                                      const int32_t *dataset_id, const double *temperature, int32_t n_datasets,
+                                      const phf_dataset *datasets, int32_t n_groups, const phf_dose_group *groups,
+                                      double *samples, int32_t n_segments, int32_t device)
+{
+    if (!cfg) return set_error(PHF_EINVAL, "phf_am_single_run_host: cfg is NULL");
+    if (cfg->model != 1 && cfg->model != 2) return set_error(PHF_EINVAL, "cfg.model must be 1 or 2");
+    if (cfg->thinning == 0) return set_error(PHF_EINVAL, "cfg.thinning must be >= 1");
+    if (device < 0 || device >= 16) return set_error(PHF_EINVAL, "device index outside 0..15");
+    if (n_chains <= 0 || n_datasets <= 0 || n_groups <= 0 || !state || !dataset_id || !temperature || !datasets ||
+        !groups)
+        return set_error(PHF_EINVAL, "phf_am_single_run_host: empty or null input");
+    if (n_segments < 1) n_segments = 1;
+    const int d = cfg->model == 1 ? 2 : 3, nf = PHF_STATE_SIZE(d);
+    cudaError_t e;
+    if ((e = cudaSetDevice(device))) return set_cuda_error(e, "cudaSetDevice");
+    Workspace &w = g_ws[device][cfg->model - 1];
+    if (!w.init) {
+        if ((e = cudaStreamCreateWithFlags(&w.compute, cudaStreamNonBlocking))) return set_cuda_error(e, "stream");
+        if ((e = cudaStreamCreateWithFlags(&w.copy, cudaStreamNonBlocking))) return set_cuda_error(e, "stream");
+        for (int i = 0; i < 2; ++i) {
+            cudaEventCreateWithFlags(&w.done[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&w.copied[i], cudaEventDisableTiming);
+        }
+        w.init = true;
+    }
+
+    // segment plan: boundaries on multiples of `thinning` so that every segment owns whole rows
+    const uint32_t total = cfg->n_iters;
+    uint32_t seg_iters = (total + n_segments - 1) / n_segments;
+    seg_iters = std::max<uint32_t>(cfg->thinning, (seg_iters + cfg->thinning - 1) / cfg->thinning * cfg->thinning);
+    const uint32_t rows_total = (cfg->t0 + total) / cfg->thinning - cfg->t0 / cfg->thinning;
+    if (samples && rows_total > cfg->rows_capacity)
+        return set_error(PHF_EINVAL, "cfg.rows_capacity is smaller than the rows this call produces");
+    const uint32_t seg_rows_cap = seg_iters / cfg->thinning + 1;
+    const size_t row_bytes = (size_t)(d + 1) * sizeof(double);
+
+    if ((e = w.state.ensure((size_t)n_chains * nf * sizeof(double))) ||
+        (e = w.dsid.ensure((size_t)n_chains * sizeof(int32_t))) ||
+        (e = w.temp.ensure((size_t)n_chains * sizeof(double))) ||
+        (e = w.datasets.ensure((size_t)n_datasets * sizeof(phf_dataset))) ||
+        (e = w.groups.ensure((size_t)n_groups * sizeof(phf_dose_group))))
+        return set_cuda_error(e, "cudaMalloc");
+    if (samples)
+        for (int i = 0; i < 2; ++i)
+            if ((e = w.samples[i].ensure((size_t)n_chains * seg_rows_cap * row_bytes)))
+                return set_cuda_error(e, "cudaMalloc(samples)");
+
+    cudaStream_t cs = w.compute;
+    cudaMemcpyAsync(w.state.p, state, (size_t)n_chains * nf * sizeof(double), cudaMemcpyHostToDevice, cs);
+    cudaMemcpyAsync(w.dsid.p, dataset_id, (size_t)n_chains * sizeof(int32_t), cudaMemcpyHostToDevice, cs);
+    cudaMemcpyAsync(w.temp.p, temperature, (size_t)n_chains * sizeof(double), cudaMemcpyHostToDevice, cs);
+    cudaMemcpyAsync(w.datasets.p, datasets, (size_t)n_datasets * sizeof(phf_dataset), cudaMemcpyHostToDevice, cs);
+    cudaMemcpyAsync(w.groups.p, groups, (size_t)n_groups * sizeof(phf_dose_group), cudaMemcpyHostToDevice, cs);
+
+    uint32_t done_iters = 0, rows_done = 0;
+    int seg = 0, rc = PHF_OK;
+    while (done_iters < total) {
+        const int b = seg & 1;
+        phf_am_config c = *cfg;
+        c.t0 = cfg->t0 + done_iters;
+        c.n_iters = std::min(seg_iters, total - done_iters);
+        c.rows_capacity = seg_rows_cap;
+        const uint32_t rows = (c.t0 + c.n_iters) / c.thinning - c.t0 / c.thinning;
+        if (samples && seg >= 2) cudaStreamWaitEvent(cs, w.copied[b], 0);  // buffer b must have been drained
+        rc = phf_am_single_run(&c, n_chains, (double *)w.state.p, (const int32_t *)w.dsid.p,
+                               (const double *)w.temp.p, (const phf_dataset *)w.datasets.p,
+                               (const phf_dose_group *)w.groups.p, samples ? (double *)w.samples[b].p : nullptr, cs);
+        if (rc != PHF_OK) break;
+        if (samples && rows > 0) {
+            cudaEventRecord(w.done[b], cs);
+            cudaStreamWaitEvent(w.copy, w.done[b], 0);
+            // device [chain][seg_rows_cap][d+1] -> host [chain][rows_capacity][d+1] at row offset rows_done
+            e = cudaMemcpy2DAsync(samples + (size_t)rows_done * (d + 1), (size_t)cfg->rows_capacity * row_bytes,
+                                  w.samples[b].p, (size_t)seg_rows_cap * row_bytes, (size_t)rows * row_bytes,
+                                  (size_t)n_chains, cudaMemcpyDeviceToHost, w.copy);
+            if (e) { rc = set_cuda_error(e, "cudaMemcpy2DAsync"); break; }
+            cudaEventRecord(w.copied[b], w.copy);
+        }
+        done_iters += c.n_iters;
+        rows_done += rows;
+        ++seg;
+    }
+    if (rc == PHF_OK)
+        cudaMemcpyAsync(state, w.state.p, (size_t)n_chains * nf * sizeof(double), cudaMemcpyDeviceToHost, cs);
+    cudaError_t e1 = cudaStreamSynchronize(cs), e2 = cudaStreamSynchronize(w.copy);
+    if (rc != PHF_OK) return rc;
+    if (e1) return set_cuda_error(e1, "phf_am_single_run_host(compute stream)");
+    if (e2) return set_cuda_error(e2, "phf_am_single_run_host(copy stream)");
+    return PHF_OK;
+}

@@ -1,0 +1,120 @@
+// Device math shared by all kernels: Philox4x32-10, Box-Muller, log Phi, Phi, Hill curve pieces.
+// fp64 throughout, no fast-math.  Reference citations are relative to the reference root.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#define PHF_DI __device__ __forceinline__
+
+namespace phf {
+
+// ---- constants: python/doseresponse.py:12-25 ----
+constexpr double kSigmaLower = 1e-3;       // sigma_uniform_lower == sigma_loc
+constexpr double kPic50ExpRate = 0.2;
+constexpr double kPic50ExpLower = -3.0;
+constexpr double kHillLower = 0.0;
+constexpr double kHillUpper = 10.0;
+constexpr double kSigmaShapeM1 = 4.0;                       // sigma_shape - 1
+constexpr double kSigmaScale = (6.0 - 1e-3) / (5.0 - 1.0);  // sigma_scale
+constexpr double kLn10Hi = 2.302585092994045901e+00;        // ln 10 rounded to double
+constexpr double kLn10Lo = -2.170756223382249351e-16;       // ln 10 - kLn10Hi
+constexpr double kSqrtHalf = 7.071067811865475244e-01;
+
+// ---- Philox4x32-10 (Salmon et al. 2011); stream contract in oracle/hill_oracle.py ----
+struct Philox4 {
+    uint32_t w[4];
+};
+
+PHF_DI Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    Philox4 o;
+    o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
+    return o;
+}
+
+PHF_DI Philox4 philox_call(uint64_t seed, uint64_t chain, uint32_t t, uint32_t j)
+{
+    return philox4x32_10(t, j, (uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// 53-bit uniform in (0,1): replaces npr.rand() (PyHillFit.py:487,834; PyHillTemp.py:100)
+PHF_DI double uniform53(uint32_t w0, uint32_t w1)
+{
+    const unsigned long long v = (((unsigned long long)w0 << 32) | w1) >> 11;
+    return fma((double)v, 0x1p-53, 0x1p-54);
+}
+
+// two standard normals from two 32-bit words
+PHF_DI void box_muller(uint32_t a, uint32_t b, double &z0, double &z1)
+{
+    const double u1 = fma((double)a, 0x1p-32, 0x1p-32);  // (a+1) 2^-32 in (0,1]
+    const double r = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi((double)b * 0x1p-31, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+// log Phi(z) for z <= 0: scipy.special.log_ndtr's x < -1 branch, log(erfcx(-z/sqrt2)/2) - z^2/2, which is
+// also accurate on [-1, 0] (the value there is in [-1.85, -0.69], no cancellation).  Call sites only ever
+// pass z = (0-p)/sigma or (p-100)/sigma with p in [0,100] (python/doseresponse.py:218-219,244-245).
+PHF_DI double log_ndtr_nonpos(double z)
+{
+    const double t = fabs(z) * kSqrtHalf;
+    return log(0.5 * erfcx(t)) - t * t;
+}
+
+// general log Phi (only used by the batch API's generality tests)
+PHF_DI double log_ndtr(double z)
+{
+    if (z <= 0.0) return log_ndtr_nonpos(z);
+    return log1p(-0.5 * erfc(z * kSqrtHalf));
+}
+
+// Phi(a): scipy.special.ndtr (cephes ndtr.c) as called by st.norm.cdf at python/PyHillFit.py:124
+PHF_DI double ndtr(double a)
+{
+    const double x = a * kSqrtHalf, z = fabs(x);
+    double y;
+    if (z < 1.0)
+        y = 0.5 + 0.5 * erf(x);
+    else {
+        y = 0.5 * erfc(z);
+        if (x > 0) y = 1.0 - y;
+    }
+    return y;
+}
+
+// ln IC50 = (6 - pIC50) ln 10 as a double-double (hi, lo): python/doseresponse.py:87-88 without the pow
+PHF_DI void ln_ic50(double pic50, double &hi, double &lo)
+{
+    const double a = 6.0 - pic50;
+    hi = a * kLn10Hi;
+    lo = fma(a, kLn10Lo, fma(a, kLn10Hi, -hi));
+}
+
+// (dose/IC50)^hill = exp(hill * (ln dose - ln IC50)) -- python/doseresponse.py:84-85.
+// 0^0 = inf^0 = 1 as numpy's power does.
+PHF_DI double hill_ratio_pow(double lnc_hi, double lnc_lo, double lic_hi, double lic_lo, double hill)
+{
+    const double L = (lnc_hi - lic_hi) + (lnc_lo - lic_lo);
+    const double x = exp(hill * L);
+    return hill == 0.0 ? 1.0 : x;
+}
+
+// predicted response 100 (1 - 1/(1 + x)) -- python/doseresponse.py:85
+PHF_DI double hill_response(double x) { return 100.0 * (1.0 - 1.0 / (1.0 + x)); }
+
+}  // namespace phf

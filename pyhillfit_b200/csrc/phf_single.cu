@@ -1,0 +1,333 @@
+// Single-level kernels: batched log-target and the fused adaptive-Metropolis sampler (one thread per chain).
+#include "phf_common.cuh"
+#include "phf_single.cuh"
+
+namespace phf {
+
+// ------------------------------------------------------------------------------------------------
+// batched log-target: one thread per parameter vector
+// ------------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(128) log_target_batch_kernel(int64_t n, const double *__restrict__ theta,
+                                                               const int32_t *__restrict__ dataset_id,
+                                                               const double *__restrict__ temperature,
+                                                               const phf_dataset *__restrict__ datasets,
+                                                               const phf_dose_group *__restrict__ groups,
+                                                               double *__restrict__ log_target,
+                                                               double *__restrict__ loglik_t1)
+{
+    constexpr int D = SingleDims<MODEL>::D;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double th[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) th[k] = theta[i * D + k];
+    const phf_dataset ds = datasets[dataset_id[i]];
+    double lt, l1;
+    single_log_target<MODEL>(th, groups + ds.group_begin, ds.n_groups, ds.pi_bit, ds.n_other_total, temperature[i],
+                             lt, l1);
+    log_target[i] = lt;
+    if (loglik_t1) loglik_t1[i] = l1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// state init: evaluate the target at theta0
+// ------------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(128) am_single_init_kernel(int64_t n, const double *__restrict__ theta0,
+                                                             const double *__restrict__ cov0,
+                                                             const int32_t *__restrict__ dataset_id,
+                                                             const double *__restrict__ temperature,
+                                                             const phf_dataset *__restrict__ datasets,
+                                                             const phf_dose_group *__restrict__ groups,
+                                                             double *__restrict__ state)
+{
+    constexpr int D = SingleDims<MODEL>::D, NT = SingleDims<MODEL>::NT, NF = SingleDims<MODEL>::NF;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double th[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) th[k] = theta0[i * D + k];
+    const phf_dataset ds = datasets[dataset_id[i]];
+    double lt, l1;
+    single_log_target<MODEL>(th, groups + ds.group_begin, ds.n_groups, ds.pi_bit, ds.n_other_total, temperature[i],
+                             lt, l1);
+    double *s = state + i * NF;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        s[k] = th[k];
+        s[D + 2 + k] = th[k];
+    }
+    s[D] = lt;
+    s[D + 1] = l1;
+#pragma unroll
+    for (int k = 0; k < NT; ++k) s[2 * D + 2 + k] = cov0[i * NT + k];
+    s[2 * D + 2 + NT] = 0.0;      // loga
+    s[2 * D + 2 + NT + 1] = 0.0;  // loglik_t1_sum
+    s[2 * D + 2 + NT + 2] = 0.0;  // n_accepted
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused adaptive Metropolis: python/PyHillFit.py:828-856 and python/PyHillTemp.py:87-123.
+// One thread per chain; theta, mean, covariance, loga, counters live in registers for all n_iters
+// iterations; the CTA's datasets are staged once in shared memory; HBM is touched only for the thinned
+// rows.  gamma_s = (s+1)^-0.6 depends on t only: lane L of each warp computes it for iteration t+L once
+// every 32 iterations and the warp reads it by shuffle.
+// ------------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void am_single_kernel(phf_am_config cfg, int64_t n, double *__restrict__ state,
+                                 const int32_t *__restrict__ dataset_id, const double *__restrict__ temperature,
+                                 const phf_dataset *__restrict__ datasets, const phf_dose_group *__restrict__ groups,
+                                 double *__restrict__ samples)
+{
+    constexpr int D = SingleDims<MODEL>::D, NT = SingleDims<MODEL>::NT, NF = SingleDims<MODEL>::NF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    phf_dose_group *sgroups = reinterpret_cast<phf_dose_group *>(smem_raw);
+
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t chain = first + threadIdx.x;
+    const bool active = chain < n;
+    const int64_t c = active ? chain : n - 1;
+    const unsigned lane = threadIdx.x & 31u;
+
+    // ---- stage this CTA's dose groups (chains are sorted by dataset, so the range is contiguous) ----
+    const phf_dataset ds = datasets[dataset_id[c]];
+    const phf_dose_group *grp = groups + ds.group_begin;
+    if (cfg.stage_groups > 0) {
+        const int64_t last = min(first + (int64_t)blockDim.x, n) - 1;
+        const phf_dataset d_lo = datasets[dataset_id[first]];
+        const phf_dataset d_hi = datasets[dataset_id[last]];
+        const int g_lo = d_lo.group_begin, g_hi = d_hi.group_begin + d_hi.n_groups;
+        const bool fits = (g_hi - g_lo) <= cfg.stage_groups && g_hi >= g_lo && ds.group_begin >= g_lo &&
+                          ds.group_begin + ds.n_groups <= g_hi;  // CTA-uniform except for unsorted input
+        const int all_fit = __syncthreads_and(fits ? 1 : 0);
+        if (all_fit) {
+            // 64-byte groups copied as 16-byte vectors, coalesced
+            const double2 *src = reinterpret_cast<const double2 *>(groups + g_lo);
+            double2 *dst = reinterpret_cast<double2 *>(sgroups);
+            const int nvec = (g_hi - g_lo) * 4;
+            for (int v = threadIdx.x; v < nvec; v += blockDim.x) dst[v] = __ldg(src + v);
+            __syncthreads();
+            grp = sgroups + (ds.group_begin - g_lo);
+        }
+    }
+    const int ng = ds.n_groups;
+    const double pi_bit = ds.pi_bit, n_other_total = ds.n_other_total;
+    const double temp = temperature[c];
+    const uint64_t chain_id = cfg.chain_id_base + (uint64_t)c;
+
+    // ---- load chain state into registers ----
+    double *sp = state + c * NF;
+    double th[D], mean[D], cov[NT];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        th[k] = sp[k];
+        mean[k] = sp[D + 2 + k];
+    }
+    double lt = sp[D], l1 = sp[D + 1];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) cov[k] = sp[2 * D + 2 + k];
+    double loga = sp[2 * D + 2 + NT];
+    double l1_sum = sp[2 * D + 2 + NT + 1];
+    double n_acc = sp[2 * D + 2 + NT + 2];
+
+    uint32_t t = cfg.t0;
+    uint32_t until_save = cfg.thinning - (t % cfg.thinning);
+    uint32_t row = t / cfg.thinning;
+    const uint32_t row_base = row + 1;
+    double *out = samples ? samples + (size_t)c * cfg.rows_capacity * (D + 1) : nullptr;
+    double gam_lane = 0.0;
+
+    for (uint32_t it = 0; it < cfg.n_iters; ++it) {
+        ++t;
+        if ((it & 31u) == 0u) {
+            const uint32_t tl = t + lane;
+            // gamma_s = 1/(s+1)**0.6, s = t - adapt_when (PyHillFit.py:841-842, PyHillTemp.py:117)
+            gam_lane = tl > cfg.adapt_when ? 1.0 / pow((double)(tl - cfg.adapt_when) + 1.0, 0.6) : 0.0;
+        }
+        const double gam = __shfl_sync(0xffffffffu, gam_lane, it & 31u);
+
+        // ---- draws: accept uniform + D normals ----
+        double z[D + 1], u;
+        {
+            const Philox4 r0 = philox_call(cfg.seed, chain_id, t, 0u);
+            u = uniform53(r0.w[0], r0.w[1]);
+            box_muller(r0.w[2], r0.w[3], z[0], z[1]);
+            if (D == 3) {
+                const Philox4 r1 = philox_call(cfg.seed, chain_id, t, 1u);
+                double unused;
+                box_muller(r1.w[0], r1.w[1], z[2], unused);
+            }
+        }
+
+        // ---- proposal theta* = theta + e^{loga/2} chol(cov) z  (N(theta, e^loga cov): PyHillFit.py:831) ----
+        double star[D];
+        {
+            const double sc = exp(0.5 * loga);
+            const double r0 = rsqrt(cov[0]);
+            const double l00 = cov[0] * r0, l10 = cov[1] * r0;
+            const double s11 = fma(-l10, l10, cov[2]);
+            const double r1 = rsqrt(s11);
+            const double l11 = s11 * r1;
+            star[0] = fma(sc, l00 * z[0], th[0]);
+            star[1] = fma(sc, fma(l10, z[0], l11 * z[1]), th[1]);
+            if (D == 3) {
+                const double l20 = cov[3] * r0;
+                const double l21 = fma(-l20, l10, cov[4]) * r1;
+                const double s22 = fma(-l21, l21, fma(-l20, l20, cov[5]));
+                const double l22 = sqrt(s22);
+                star[D - 1] = fma(sc, fma(l20, z[0], fma(l21, z[1], l22 * z[2])), th[D - 1]);
+            }
+        }
+
+        // ---- target, accept (PyHillFit.py:833-838) ----
+        double lt_star, l1_star;
+        single_log_target<MODEL>(star, grp, ng, pi_bit, n_other_total, temp, lt_star, l1_star);
+        const bool accepted = log(u) < lt_star - lt;
+        if (accepted) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) th[k] = star[k];
+            lt = lt_star;
+            l1 = l1_star;
+            n_acc += 1.0;
+        }
+
+        // ---- adaptation (PyHillFit.py:840-846; PyHillTemp.py:114-122) ----
+        if (cfg.reset_mean_at_adapt && t == cfg.adapt_when) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) mean[k] = th[k];
+        }
+        if (t > cfg.adapt_when) {
+            const double omg = 1.0 - gam;
+            double dv[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) dv[k] = th[k] - mean[k];
+            int q = 0;
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j, ++q) cov[q] = fma(gam, dv[i] * dv[j], omg * cov[q]);
+#pragma unroll
+            for (int k = 0; k < D; ++k) mean[k] = fma(gam, th[k], omg * mean[k]);
+            loga = fma(gam, (accepted ? 1.0 : 0.0) - 0.25, loga);
+        }
+
+        // ---- thinned write-out (PyHillFit.py:847-848) + Sum loglik_t1 for thermodynamic integration ----
+        if (--until_save == 0u) {
+            until_save = cfg.thinning;
+            ++row;
+            if (out && active) {
+                double *o = out + (size_t)(row - row_base) * (D + 1);
+#pragma unroll
+                for (int k = 0; k < D; ++k) o[k] = th[k];
+                o[D] = lt;
+            }
+            if (row >= cfg.burn_rows) l1_sum += l1;
+        }
+    }
+
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            sp[k] = th[k];
+            sp[D + 2 + k] = mean[k];
+        }
+        sp[D] = lt;
+        sp[D + 1] = l1;
+#pragma unroll
+        for (int k = 0; k < NT; ++k) sp[2 * D + 2 + k] = cov[k];
+        sp[2 * D + 2 + NT] = loga;
+        sp[2 * D + 2 + NT + 1] = l1_sum;
+        sp[2 * D + 2 + NT + 2] = n_acc;
+    }
+}
+
+}  // namespace phf
+
+using namespace phf;
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int phf_log_target_batch(int model, int64_t n, const double *theta, const int32_t *dataset_id,
+                                    const double *temperature, const phf_dataset *datasets,
+                                    const phf_dose_group *groups, double *log_target, double *loglik_t1, void *stream)
+{
+    if (model != 1 && model != 2) return set_error(PHF_EINVAL, "model must be 1 or 2");
+    if (n < 0 || (n > 0 && (!theta || !dataset_id || !temperature || !datasets || !groups || !log_target)))
+        return set_error(PHF_EINVAL, "phf_log_target_batch: null pointer");
+    if (n == 0) return PHF_OK;
+    const int block = 128;
+    const unsigned grid = (unsigned)((n + block - 1) / block);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (model == 1)
+        log_target_batch_kernel<1><<<grid, block, 0, s>>>(n, theta, dataset_id, temperature, datasets, groups,
+                                                          log_target, loglik_t1);
+    else
+        log_target_batch_kernel<2><<<grid, block, 0, s>>>(n, theta, dataset_id, temperature, datasets, groups,
+                                                          log_target, loglik_t1);
+    count_launch();
+    return check_launch("log_target_batch_kernel");
+}
+
+extern "C" int phf_am_single_init(int model, int64_t n_chains, const double *theta0, const double *cov0_tri,
+                                  const int32_t *dataset_id, const double *temperature, const phf_dataset *datasets,
+                                  const phf_dose_group *groups, double *state, void *stream)
+{
+    if (model != 1 && model != 2) return set_error(PHF_EINVAL, "model must be 1 or 2");
+    if (n_chains < 0 || (n_chains > 0 && (!theta0 || !cov0_tri || !dataset_id || !temperature || !datasets ||
+                                          !groups || !state)))
+        return set_error(PHF_EINVAL, "phf_am_single_init: null pointer");
+    if (n_chains == 0) return PHF_OK;
+    const int block = 128;
+    const unsigned grid = (unsigned)((n_chains + block - 1) / block);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (model == 1)
+        am_single_init_kernel<1><<<grid, block, 0, s>>>(n_chains, theta0, cov0_tri, dataset_id, temperature,
+                                                        datasets, groups, state);
+    else
+        am_single_init_kernel<2><<<grid, block, 0, s>>>(n_chains, theta0, cov0_tri, dataset_id, temperature,
+                                                        datasets, groups, state);
+    count_launch();
+    return check_launch("am_single_init_kernel");
+}
+
+extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, double *state,
+                                 const int32_t *dataset_id, const double *temperature, const phf_dataset *datasets,
+                                 const phf_dose_group *groups, double *samples, void *stream)
+{
+    if (!cfg) return set_error(PHF_EINVAL, "phf_am_single_run: cfg is NULL");
+    if (cfg->model != 1 && cfg->model != 2) return set_error(PHF_EINVAL, "cfg.model must be 1 or 2");
+    if (cfg->thinning == 0) return set_error(PHF_EINVAL, "cfg.thinning must be >= 1");
+    if (n_chains < 0 || (n_chains > 0 && (!state || !dataset_id || !temperature || !datasets || !groups)))
+        return set_error(PHF_EINVAL, "phf_am_single_run: null pointer");
+    if ((uint64_t)cfg->t0 + cfg->n_iters > 0xFFFFFFFFull) return set_error(PHF_EINVAL, "iteration counter overflow");
+    const uint32_t rows = (cfg->t0 + cfg->n_iters) / cfg->thinning - cfg->t0 / cfg->thinning;
+    if (samples && rows > cfg->rows_capacity)
+        return set_error(PHF_EINVAL, "cfg.rows_capacity is smaller than the rows this call produces");
+    if (n_chains == 0 || cfg->n_iters == 0) return PHF_OK;
+
+    int block = cfg->block_threads;
+    if (block <= 0) block = default_block_threads(n_chains);
+    if (block % 32 != 0 || block > 1024) return set_error(PHF_EINVAL, "cfg.block_threads must be a multiple of 32");
+    const size_t smem = cfg->stage_groups > 0 ? (size_t)cfg->stage_groups * sizeof(phf_dose_group) : 0;
+    if (smem > 200 * 1024) return set_error(PHF_EINVAL, "cfg.stage_groups needs more than 200 KB of shared memory");
+    const unsigned grid = (unsigned)((n_chains + block - 1) / block);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e;
+    if (cfg->model == 1) {
+        if (smem > 48 * 1024 &&
+            (e = cudaFuncSetAttribute(am_single_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)))
+            return set_cuda_error(e, "cudaFuncSetAttribute");
+        am_single_kernel<1><<<grid, block, smem, s>>>(*cfg, n_chains, state, dataset_id, temperature, datasets,
+                                                      groups, samples);
+    } else {
+        if (smem > 48 * 1024 &&
+            (e = cudaFuncSetAttribute(am_single_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)))
+            return set_cuda_error(e, "cudaFuncSetAttribute");
+        am_single_kernel<2><<<grid, block, smem, s>>>(*cfg, n_chains, state, dataset_id, temperature, datasets,
+                                                      groups, samples);
+    }
+    count_launch();
+    return check_launch("am_single_kernel");
+}

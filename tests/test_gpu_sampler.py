@@ -1,0 +1,191 @@
+"""GPU tests of the fused adaptive-Metropolis kernels: step-by-step trajectory parity with the C oracle on
+the shared Philox stream, launch-segmentation invariance, the host-buffer entry point, and statistical
+parity with chains produced by the unmodified reference (tests/golden/ref_chains.npz)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import c_oracle
+import hill_oracle as ho
+from _data import GOLD, Table
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def table():
+    return Table("crumb_data")
+
+
+def _oracle_chain(model, concs, y, temp, theta0, cov0, iters, thin, adapt_when, reset, seed, chain_id):
+    pb = ho.compute_pi_bit_of_log_likelihood(y)
+    lt0, l10 = c_oracle.log_target_batch(model, concs, y, theta0[None, :], temp, pb)
+    st = c_oracle.make_state(theta0, lt0[0], l10[0], cov0)
+    chain = c_oracle.am_single(model, concs, y, temp, pb, st, 0, iters, thin, adapt_when, reset, seed, chain_id)
+    return chain, st
+
+
+@pytest.mark.parametrize("model,variant", [(2, "temp"), (2, "fit"), (1, "fit"), (1, "temp")])
+def test_single_level_trajectories_follow_oracle(table, model, variant):
+    """Same seed, same Philox counters, same algorithm: the GPU chain and the C oracle chain agree row by row
+    (until fp64 rounding differences flip an accept, which the tolerance window below does not reach)."""
+    from pyhillfit_b200.packing import SinglePack
+    from pyhillfit_b200.sampler import SingleLevelSampler, variant_defaults
+    pairs = [("Amiodarone", "hERG"), ("Bepridil", "hERG"), ("Amitriptyline", "Kv4.3"), ("Dofetilide", "hERG")]
+    pack = SinglePack([table.concat(d, c) for d, c in pairs])
+    d = 2 if model == 1 else 3
+    temps = [1.0, 0.421875, 0.0, 0.015625] if variant == "temp" else [1.0] * 4
+    n_per = 3
+    ids = np.repeat(np.arange(len(pairs), dtype=np.int32), n_per)
+    tt = np.repeat(temps, n_per)
+    rng = np.random.default_rng(5)
+    if variant == "temp":
+        theta0 = np.ones((len(ids), d))
+    else:
+        theta0 = np.stack([rng.uniform(4.5, 6.5, len(ids)), rng.uniform(0.6, 1.4, len(ids)),
+                           rng.uniform(4, 9, len(ids))], 1)
+        theta0 = theta0 if model == 2 else theta0[:, [0, 2]]
+    iters, thin, adapt_when, seed, base = 600, 5, 100, 77, 1000
+    s = SingleLevelSampler(model, pack, ids, tt, theta0, variant=variant, adapt_when=adapt_when, seed=seed,
+                           chain_id_base=base, thinning=thin, burn_rows=20)
+    row0 = s.initial_row().cpu().numpy()
+    got = s.run(iters).cpu().numpy()
+    f = s.state_fields()
+    cov0, _, reset = variant_defaults(variant, theta0)
+    for k in range(len(ids)):
+        concs, y = table.concat(*pairs[ids[k]])
+        want, st = _oracle_chain(model, concs, y, tt[k], theta0[k], cov0[k], iters, thin, adapt_when, reset, seed,
+                                 base + k)
+        assert np.allclose(row0[k, :d], theta0[k]) and row0[k, d] == pytest.approx(
+            c_oracle.log_target_batch(model, concs, y, theta0[k][None], tt[k],
+                                      ho.compute_pi_bit_of_log_likelihood(y))[0][0], rel=1e-12)
+        assert np.allclose(got[k], want, rtol=1e-8, atol=1e-8), "chain %d diverged from the oracle" % k
+        assert f["n_accepted"][k] == st[-1]
+        assert f["loga"][k] == pytest.approx(st[-3], rel=1e-9, abs=1e-9)
+        assert np.allclose(f["cov"][k].reshape(-1), st[2 * d + 2:2 * d + 2 + d * d], rtol=1e-7, atol=1e-12)
+        assert np.allclose(f["mean"][k], st[d + 2:2 * d + 2], rtol=1e-8)
+    # thermodynamic-integration accumulator == mean of the oracle's temperature-1 log-likelihood over rows >= burn
+    concs, y = table.concat(*pairs[0])
+    want, _ = _oracle_chain(model, concs, y, tt[0], theta0[0], cov0[0], iters, thin, adapt_when, reset, seed, base)
+    _, l1 = c_oracle.log_target_batch(model, concs, y, np.ascontiguousarray(want[19:, :d]), 1.0,
+                                      ho.compute_pi_bit_of_log_likelihood(y))
+    assert s.loglik_t1_mean()[0] == pytest.approx(l1.mean(), rel=1e-9)
+
+
+def test_segmented_launches_are_bit_identical(table):
+    from pyhillfit_b200.packing import SinglePack
+    from pyhillfit_b200.sampler import SingleLevelSampler
+    pack = SinglePack([table.concat(d, c) for d, c in table.pairs()[:40]])
+    ids = np.repeat(np.arange(40, dtype=np.int32), 5)
+    theta0 = np.tile([5.5, 1.0, 6.0], (len(ids), 1))
+    kw = dict(variant="fit", adapt_when=300, seed=3, thinning=5, burn_rows=0)
+    a = SingleLevelSampler(2, pack, ids, 1.0, theta0, **kw)
+    whole = a.run(2000).cpu().numpy()
+    b = SingleLevelSampler(2, pack, ids, 1.0, theta0, stage=False, block_threads=64, **kw)
+    parts = [b.run(k).cpu().numpy() for k in (5, 700, 33, 1262)]   # 33: segment boundary off the thinning grid
+    assert np.array_equal(whole, np.concatenate(parts, axis=1))
+    assert np.array_equal(a.state.cpu().numpy(), b.state.cpu().numpy())
+    assert whole.shape == (200, 400, 4)
+    acc = a.acceptance()
+    assert 0.05 < acc.mean() < 0.6
+
+
+def test_host_buffer_entry_point(table):
+    """phf_am_single_run_host: numpy in, numpy out, identical to the device-pointer path."""
+    import torch
+    from pyhillfit_b200 import _lib
+    from pyhillfit_b200.packing import SinglePack
+    from pyhillfit_b200.sampler import SingleLevelSampler
+    pack = SinglePack([table.concat(d, c) for d, c in table.pairs()[:16]])
+    ids = np.repeat(np.arange(16, dtype=np.int32), 8)
+    theta0 = np.tile([5.5, 1.0, 6.0], (len(ids), 1))
+    kw = dict(variant="fit", adapt_when=200, seed=11, thinning=5, burn_rows=10)
+    ref = SingleLevelSampler(2, pack, ids, 1.0, theta0, **kw)
+    state0 = ref.state.cpu().numpy().copy()
+    want = ref.run(1000).cpu().numpy()
+    state = torch.from_numpy(state0.copy()).pin_memory().numpy()
+    rows = 200
+    samples = torch.empty((len(ids), rows, 4), dtype=torch.float64).pin_memory().numpy()
+    cfg = _lib.AmConfig(model=2, reset_mean_at_adapt=0, t0=0, n_iters=1000, thinning=5, adapt_when=200, burn_rows=10,
+                        rows_capacity=rows, seed=11, chain_id_base=0, stage_groups=0, block_threads=0)
+    temps = np.ones(len(ids))
+    L = _lib.load()
+    _lib.check(L.phf_am_single_run_host(C.byref(cfg), len(ids), state.ctypes.data, ids.ctypes.data,
+                                        temps.ctypes.data, pack.n_datasets, pack.datasets.ctypes.data,
+                                        len(pack.groups), pack.groups.ctypes.data, samples.ctypes.data, 4, 0),
+               "phf_am_single_run_host")
+    assert np.array_equal(samples, want)
+    assert np.array_equal(state, ref.state.cpu().numpy())
+
+
+def test_hier_trajectories_follow_oracle(table):
+    from pyhillfit_b200.packing import HierPack
+    from pyhillfit_b200.sampler import HierarchicalSampler, hier_priors, variant_defaults
+    pr, shapes, scales, locs = hier_priors()
+    pairs = table.pairs()
+    by_ne = {}
+    for ip, (d, c) in enumerate(pairs):
+        by_ne.setdefault(len(table.experiments(d, c)), []).append(ip)
+    assert sorted(by_ne) == [3, 4, 5, 6]
+    for ne, idxs in sorted(by_ne.items()):
+        use = idxs[:3]
+        pack = HierPack([table.experiments(*pairs[i]) for i in use])
+        ids = np.repeat(np.arange(len(use), dtype=np.int32), 2)
+        dim = 5 + 2 * ne
+        rng = np.random.default_rng(ne)
+        theta0 = np.concatenate([np.tile([1.0, 4.0, 6.0, 0.3], (len(ids), 1)),
+                                 np.tile([5.0, 1.0], (len(ids), ne)) + rng.uniform(-0.3, 0.3, (len(ids), 2 * ne)),
+                                 np.full((len(ids), 1), 8.0)], axis=1)
+        iters, thin, adapt_when, seed, base = 300, 5, 60, 5, 10 ** 10
+        s = HierarchicalSampler(pack, ids, theta0, pr, adapt_when=adapt_when, seed=seed, chain_id_base=base,
+                                thinning=thin)
+        lt0 = s.initial_row().cpu().numpy()[:, dim]
+        got = s.run(iters).cpu().numpy()
+        cov0, _, _ = variant_defaults("hier", theta0)
+        f = s.state_fields()
+        for k in range(len(ids)):
+            ex = table.experiments(*pairs[use[ids[k]]])
+            want0 = c_oracle.hier_log_target_batch(ex, theta0[k][None], shapes, scales, locs)[0]
+            assert lt0[k] == pytest.approx(want0, rel=1e-12)
+            st = c_oracle.make_state(theta0[k], want0, 0.0, cov0[k])
+            want = c_oracle.am_hier(ex, shapes, scales, locs, st, 0, iters, thin, adapt_when, seed, base + k)
+            assert np.allclose(got[k], want, rtol=1e-7, atol=1e-7), "ne=%d chain %d diverged" % (ne, k)
+            assert f["n_accepted"][k] == st[-1]
+
+
+def _quantile_check(samples, q_ref, sd_ref, ess_ref, n_sigma=5.0):
+    """GPU pooled quantiles vs reference quantiles, tolerance n_sigma * reference MCSE (quantile MCSE ~
+    1.6 sd / sqrt(ESS) for the 5/95 % points, 1.25 for the median; use the larger)."""
+    q = np.percentile(samples, [5, 25, 50, 75, 95], axis=0)
+    tol = n_sigma * 1.7 * sd_ref / np.sqrt(ess_ref)
+    assert np.all(np.abs(q - q_ref) <= tol[None, :]), (q, q_ref, tol)
+
+
+@pytest.mark.parametrize("model", [1, 2])
+def test_posterior_quantiles_match_reference_chains(table, model):
+    """64 GPU chains per temperature vs the reference's do_mcmc chain (PyHillTemp.py:57-125, numpy RNG)."""
+    from pyhillfit_b200.packing import SinglePack
+    from pyhillfit_b200.sampler import SingleLevelSampler
+    g = np.load(os.path.join(GOLD, "ref_chains.npz"))
+    temps = g["temps"]
+    sel = [40, 30, 20, 10, 0]
+    pack = SinglePack([table.concat("Amiodarone", "hERG")])
+    d = 2 if model == 1 else 3
+    nch = 64
+    tt = np.repeat(temps[sel], nch)
+    iters, thin = 40000, 5
+    burn = (iters // thin + 1) // 4
+    s = SingleLevelSampler(model, pack, np.zeros(len(tt), dtype=np.int32), tt, np.ones((len(tt), d)), variant="temp",
+                           seed=2024, thinning=thin, burn_rows=burn)
+    smp = s.run(iters).cpu().numpy()[:, burn - 1:, :]
+    ll1 = s.loglik_t1_mean().reshape(len(sel), nch)
+    for j, it in enumerate(sel):
+        pooled = smp[j * nch:(j + 1) * nch, :, :d].reshape(-1, d)
+        _quantile_check(pooled, g["ladder_m%d_q" % model][it], g["ladder_m%d_sd" % model][it],
+                        g["ladder_m%d_ess" % model][it])
+        ref_m, ref_se = g["ladder_m%d_ll1_mean" % model][it], g["ladder_m%d_ll1_sd" % model][it] / np.sqrt(
+            g["ladder_m%d_ll1_ess" % model][it])
+        gpu_se = ll1[j].std(ddof=1) / np.sqrt(nch)
+        assert abs(ll1[j].mean() - ref_m) <= 5 * np.hypot(ref_se, gpu_se) + 1e-9, (it, ll1[j].mean(), ref_m, ref_se)
