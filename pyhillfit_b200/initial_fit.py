@@ -24,11 +24,12 @@ def sum_of_square_diffs(params, concs, responses):
     return float(np.sum((_curve(concs, hill, pic50) - responses) ** 2))
 
 
-def best_fit(model, concs, responses):
+def best_fit(model, concs, responses, pic50_lower=PIC50_LOWER):
     """-> theta0: (pIC50, sigma) for model 1, (pIC50, Hill, sigma) for model 2, and the sum of squares."""
     concs = np.asarray(concs, dtype=float)
     responses = np.asarray(responses, dtype=float)
-    pic50_grid = np.linspace(PIC50_LOWER, 12.0, 61)
+    PL = pic50_lower
+    pic50_grid = np.linspace(PL, 12.0, 61)
     hill_grid = np.array([1.0]) if model == 1 else np.array([0.25, 0.5, 0.75, 1.0, 1.5, 2.0, 3.0, 5.0])
     best = (np.inf, None)
     for h in hill_grid:
@@ -38,15 +39,15 @@ def best_fit(model, concs, responses):
                 best = (ss, (p, h))
     p0, h0 = best[1]
     if model == 1:
-        obj = lambda x: sum_of_square_diffs((x[0] ** 2 + PIC50_LOWER, 1.0), concs, responses)
-        res = minimize(obj, [np.sqrt(p0 - PIC50_LOWER)], method="Nelder-Mead",
+        obj = lambda x: sum_of_square_diffs((x[0] ** 2 + PL, 1.0), concs, responses)
+        res = minimize(obj, [np.sqrt(p0 - PL)], method="Nelder-Mead",
                        options=dict(xatol=1e-10, fatol=1e-12, maxiter=4000))
-        pic50, hill, ss = res.x[0] ** 2 + PIC50_LOWER, 1.0, res.fun
+        pic50, hill, ss = res.x[0] ** 2 + PL, 1.0, res.fun
     else:
-        obj = lambda x: sum_of_square_diffs((x[0] ** 2 + PIC50_LOWER, x[1] ** 2 + HILL_LOWER), concs, responses)
-        res = minimize(obj, [np.sqrt(p0 - PIC50_LOWER), np.sqrt(h0 - HILL_LOWER)], method="Nelder-Mead",
+        obj = lambda x: sum_of_square_diffs((x[0] ** 2 + PL, x[1] ** 2 + HILL_LOWER), concs, responses)
+        res = minimize(obj, [np.sqrt(p0 - PL), np.sqrt(h0 - HILL_LOWER)], method="Nelder-Mead",
                        options=dict(xatol=1e-10, fatol=1e-12, maxiter=8000))
-        pic50, hill, ss = res.x[0] ** 2 + PIC50_LOWER, res.x[1] ** 2 + HILL_LOWER, res.fun
+        pic50, hill, ss = res.x[0] ** 2 + PL, res.x[1] ** 2 + HILL_LOWER, res.fun
     if ss > best[0]:
         pic50, hill, ss = p0, h0, best[0]
     sigma = np.sqrt(ss / len(responses))  # initial_sigma, python/PyHillFit.py:101-102
