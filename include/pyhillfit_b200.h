@@ -100,7 +100,11 @@ typedef struct phf_am_config {
     uint64_t seed;
     uint64_t chain_id_base;      /* global id of local chain 0 (ranks shard one global chain list) */
     int32_t stage_groups;        /* shared-memory staging capacity per CTA in dose groups / points (0: read via L1) */
-    int32_t block_threads;       /* 0: library default */
+    int32_t block_threads;       /* 0: library default (threads per CTA, multiple of 32, <= 128) */
+    int32_t lanes_per_chain;     /* single-level only: 1, 2 or 4 lanes cooperate on one chain; 0: chosen from
+                                    n_chains (phf_am_single_lanes).  Results of different lane counts agree to
+                                    rounding (the reduction order differs), not bit for bit. */
+    int32_t reserved;
 } phf_am_config;
 
 /* Evaluate the target at theta0 and fill `state` (mean = theta0, cov = cov0, loga = 0, counters = 0). */
@@ -109,10 +113,13 @@ int phf_am_single_init(int model, int64_t n_chains, const double *theta0 /* [n,d
                        const double *temperature, const phf_dataset *datasets, const phf_dose_group *groups,
                        double *state /* [n, PHF_STATE_SIZE(d)] */, void *stream);
 
+/* lanes per chain the library picks for `n_chains` when cfg->lanes_per_chain == 0 (current device) */
+int phf_am_single_lanes(int64_t n_chains);
+
 /*
  * Run cfg->n_iters iterations of every chain.  `samples` ([n_chains, rows_capacity, d+1], may be NULL)
  * receives (theta, log_target) for each saved row of this call: local row = t/thinning - t0/thinning - 1.
- * Chains must be sorted by dataset_id when cfg->stage_groups > 0.
+ * Chains must be sorted by dataset_id when cfg->stage_groups > 0 (a CTA of B threads covers B / lanes chains).
  */
 int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, double *state, const int32_t *dataset_id,
                       const double *temperature, const phf_dataset *datasets, const phf_dose_group *groups,

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphf_b200.so")
+LIB_PATH = os.environ.get("PHF_B200_LIB") or os.path.join(_HERE, "libphf_b200.so")  # env: developer A/B builds
 
 PHF_OK = 0
 
@@ -22,7 +22,8 @@ class AmConfig(C.Structure):
     _fields_ = [("model", C.c_int32), ("reset_mean_at_adapt", C.c_int32), ("t0", C.c_uint32),
                 ("n_iters", C.c_uint32), ("thinning", C.c_uint32), ("adapt_when", C.c_uint32),
                 ("burn_rows", C.c_uint32), ("rows_capacity", C.c_uint32), ("seed", C.c_uint64),
-                ("chain_id_base", C.c_uint64), ("stage_groups", C.c_int32), ("block_threads", C.c_int32)]
+                ("chain_id_base", C.c_uint64), ("stage_groups", C.c_int32), ("block_threads", C.c_int32),
+                ("lanes_per_chain", C.c_int32), ("reserved", C.c_int32)]
 
 
 class HierPriors(C.Structure):
@@ -41,7 +42,7 @@ HIER_DATASET_DTYPE = np.dtype([("point_begin", "<i4"), ("n_points", "<i4"), ("n_
 assert DOSE_GROUP_DTYPE.itemsize == 64 and DATASET_DTYPE.itemsize == 32
 assert HIER_POINT_DTYPE.itemsize == 32 and HIER_DATASET_DTYPE.itemsize == 16
 
-EXPORTS = ["phf_log_target_batch", "phf_am_single_init", "phf_am_single_run", "phf_hier_log_target_batch",
+EXPORTS = ["phf_log_target_batch", "phf_am_single_init", "phf_am_single_run", "phf_am_single_lanes", "phf_hier_log_target_batch",
            "phf_am_hier_init", "phf_am_hier_run", "phf_am_single_run_host", "phf_version", "phf_last_error",
            "phf_fp64_peak_probe", "phf_launch_count"]
 
@@ -68,6 +69,7 @@ def load():
     L.phf_fp64_peak_probe.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.phf_log_target_batch.argtypes = [C.c_int, C.c_int64, _p, _p, _p, _p, _p, _p, _p, _p]
     L.phf_am_single_init.argtypes = [C.c_int, C.c_int64, _p, _p, _p, _p, _p, _p, _p, _p]
+    L.phf_am_single_lanes.argtypes = [C.c_int64]
     L.phf_am_single_run.argtypes = [C.POINTER(AmConfig), C.c_int64, _p, _p, _p, _p, _p, _p, _p]
     L.phf_hier_log_target_batch.argtypes = [C.c_int64, _p, C.c_int32, _p, _p, _p, C.POINTER(HierPriors), _p, _p]
     L.phf_am_hier_init.argtypes = [C.c_int32, C.c_int64, _p, _p, _p, _p, _p, C.POINTER(HierPriors), _p, _p]

@@ -1,0 +1,293 @@
+// fp64 elementary functions written for the fused samplers' inner loops.
+//
+// Why not the CUDA math library: one adaptive-Metropolis iteration is a chain of ~15 transcendental calls, and
+// on sm_100a the library versions spend about two thirds of their issue slots outside the FP64 pipe -- every
+// 64-bit polynomial coefficient is materialised by two UMOV instructions, every divide / sqrt carries a
+// branch to a slow path, and each function re-derives special cases (NaN, denormals, negative arguments) that
+// cannot occur here.  These versions
+//   * take their coefficients from one 480-byte table staged in SHARED memory (one LDS.128 brings two of them;
+//     ptxas turns __constant__ reads into one LDC.64 per coefficient and parks them in vector registers),
+//   * are branch-free and evaluated with Estrin's scheme (short dependent chains),
+//   * use the MUFU seeds (rcp.approx / rsqrt.approx) with FMA Newton steps instead of IEEE division / sqrt,
+//   * state their domain instead of handling everything.
+// Accuracy: every function is within a few ulp on its domain (tests/test_fastmath.py measures it on the host
+// build of this same header against mpmath / libm); the log-target built from them stays within the 1e-12
+// parity bound with two orders of magnitude to spare.
+//
+// The header also compiles as plain C++ (g++) for the host accuracy tests; there the MUFU seeds are emulated by
+// a 20-bit reciprocal.  Coefficients: scripts/gen_fastmath_coeffs.py -> phf_fastmath_coeffs.inc.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+// where the kernels read the coefficients from: 0 = __constant__ memory, 1 = a shared-memory copy (LDS.128
+// pairs), 2 = literals (constexpr table folded into immediates)
+#ifndef PHF_FM_TABLE_MODE
+#define PHF_FM_TABLE_MODE 0
+#endif
+#if defined(__CUDACC__)
+#define PHF_FM __device__ __forceinline__
+#if PHF_FM_TABLE_MODE == 2
+#define PHF_COEFF_TABLE static __device__ const
+#else
+#define PHF_COEFF_TABLE static __constant__ __align__(16)
+#endif
+#else
+#define PHF_FM static inline
+#define PHF_COEFF_TABLE alignas(16) static const
+struct double2 {
+    double x, y;
+};
+#endif
+
+namespace phf {
+namespace fm {
+
+#include "phf_fastmath_coeffs.inc"
+
+// Every function below takes `T`, the base of the coefficient table: shared memory in the kernels (see
+// stage_table), kFmTable itself in the host build.
+#if defined(__CUDACC__) && PHF_FM_TABLE_MODE == 1
+// Copy the table into shared memory; call from all threads of the CTA, then __syncthreads().
+__device__ __forceinline__ void stage_table(double *smem_table)
+{
+    for (int i = threadIdx.x; i < PHF_FM_TABLE_SIZE; i += blockDim.x) smem_table[i] = kFmTable[i];
+}
+#endif
+
+// ---- bit access -------------------------------------------------------------------------------
+PHF_FM int hi_word(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x);
+#else
+    uint64_t u;
+    std::memcpy(&u, &x, 8);
+    return (int)(u >> 32);
+#endif
+}
+PHF_FM int lo_word(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2loint(x);
+#else
+    uint64_t u;
+    std::memcpy(&u, &x, 8);
+    return (int)(u & 0xffffffffu);
+#endif
+}
+PHF_FM double make_double(int hi, int lo)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, lo);
+#else
+    uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double x;
+    std::memcpy(&x, &u, 8);
+    return x;
+#endif
+}
+
+// ---- MUFU seeds: ~20 good bits, low word of the result is zero ----------------------------------
+PHF_FM double rcp_seed(double a)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    return y;
+#else
+    const double t = 1.0 / make_double(hi_word(a), 0);
+    return make_double(hi_word(t), 0);
+#endif
+}
+PHF_FM double rsqrt_seed(double a)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    return y;
+#else
+    const double t = 1.0 / std::sqrt(make_double(hi_word(a), 0));
+    return make_double(hi_word(t), 0);
+#endif
+}
+
+// ---- Estrin evaluation of sum_{k=LO..HI} c[k] x^(k-LO); xp[j] = x^(2^j) --------------------------
+template <int N>
+struct FloorLog2 {
+    static constexpr int value = 1 + FloorLog2<(N >> 1)>::value;
+};
+template <>
+struct FloorLog2<1> {
+    static constexpr int value = 0;
+};
+
+template <int LO, int HI>
+PHF_FM double poly(const double *c, const double *xp)
+{
+    if constexpr (LO == HI) {
+        return c[LO];
+    } else if constexpr (HI == LO + 1) {
+        static_assert((LO & 1) == 0, "coefficient pairs are 16-byte aligned");
+#if PHF_FM_TABLE_MODE == 1
+        const double2 p = *reinterpret_cast<const double2 *>(c + LO);  // one 128-bit load brings both
+        return fma(p.y, xp[0], p.x);
+#else
+        return fma(c[HI], xp[0], c[LO]);
+#endif
+    } else {
+        constexpr int j = FloorLog2<HI - LO>::value;  // 2^j = largest power of two <= HI-LO, i.e. < number of terms
+        constexpr int half = 1 << j;
+        return fma(poly<LO + half, HI>(c, xp), xp[j], poly<LO, LO + half - 1>(c, xp));
+    }
+}
+
+// ---- 1/a, a finite and normal (|a| in [1e-290, 1e290]); <= 1 ulp ---------------------------------
+PHF_FM double rcp(double a)
+{
+    double y = rcp_seed(a);
+    double e = fma(-a, y, 1.0);
+    e = fma(e, e, e);
+    y = fma(y, e, y);  // relative error ~2^-60
+    e = fma(-a, y, 1.0);
+    return fma(y, e, y);
+}
+
+// ---- 1/sqrt(a), a > 0 normal --------------------------------------------------------------------
+PHF_FM double rsqrt(double a)
+{
+    double y = rsqrt_seed(a);
+    const double h = 0.5 * a;
+    double e = fma(-(h * y), y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-(h * y), y, 0.5);
+    return fma(y, e, y);
+}
+
+// ---- sqrt(a), a >= 0 (a == 0 -> 0) --------------------------------------------------------------
+PHF_FM double sqrt_nonneg(double a)
+{
+    const double y = rsqrt_seed(fmax(a, 1e-290));
+    double g = a * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    return fma(g, r, g);
+}
+
+// ---- exp(x); the argument is clamped to [-700, 700] (the callers' results saturate long before) -----
+PHF_FM double exp_clamped(const double *T, double x)
+{
+    const double kLog2eHi = 1.4426946640014648;       // 0x3ff7154700000000: log2(e) to 21 bits (picks n only)
+    const double kLn2Hi = 0.693147182464599609375;    // 0x3fe62e4300000000: n * kLn2Hi is exact
+    const double kLn2Lo = T[PHF_FM_KMISC + 0];         // ln 2 - kLn2Hi
+    const double kMagic = 6755399441055744.0;         // 1.5 * 2^52
+    x = fmin(fmax(x, -700.0), 700.0);
+    const double t = fma(x, kLog2eHi, kMagic);
+    const int n = lo_word(t);
+    const double nf = t - kMagic;
+    double r = fma(nf, -kLn2Hi, x);
+    r = fma(nf, -kLn2Lo, r);
+    double xp[4];
+    xp[0] = r;
+    xp[1] = r * r;
+    xp[2] = xp[1] * xp[1];
+    xp[3] = xp[2] * xp[2];
+    const double q = poly<0, 9>(T + PHF_FM_KEXPQ, xp);
+    const double p = fma(xp[1], q, r);                 // e^r - 1
+    const double s = make_double((n + 1023) << 20, 0);  // 2^n, n in [-1010, 1010]
+    return fma(s, p, s);
+}
+
+// ---- log(x), x positive and normal --------------------------------------------------------------
+PHF_FM double log_pos(const double *T, double x)
+{
+    const double kLn2Hi = 0.693147182464599609375;
+    const double kLn2Lo = T[PHF_FM_KMISC + 0];
+    // mantissa to [sqrt(1/2), sqrt(2)): 0x3fe6a09e is the high word of sqrt(1/2)
+    const int k = hi_word(x) + (0x3ff00000 - 0x3fe6a09e);
+    const int e = (k >> 20) - 1023;
+    const double m = make_double((k & 0x000fffff) + 0x3fe6a09e, lo_word(x));
+    const double num = m - 1.0, den = m + 1.0;
+    // f = num / den
+    double y = rcp_seed(den);
+    double d = fma(-den, y, 1.0);
+    d = fma(d, d, d);
+    y = fma(y, d, y);
+    double f = num * y;
+    f = fma(fma(-f, den, num), y, f);
+    double xp[3];
+    xp[0] = f * f;
+    xp[1] = xp[0] * xp[0];
+    xp[2] = xp[1] * xp[1];
+    const double R = poly<0, 6>(T + PHF_FM_KLOGR, xp);
+    const double ef = (double)e;
+    // log x = e ln2 + 2 atanh(f) = e ln2_hi + (2f + (f^3 R + e ln2_lo))
+    const double tail = fma(f * xp[0], R, ef * kLn2Lo);
+    return fma(ef, kLn2Hi, fma(2.0, f, tail));
+}
+
+// ---- erfcx(t) = exp(t^2) erfc(t), t >= 0 ----------------------------------------------------------
+// erfcx(t) (1 + 2t) = P(q), q = (t - K)/(t + K): one polynomial on q in [-1, 1) covers the half line.
+PHF_FM double erfcx_nonneg(const double *T, double t)
+{
+    t = fmin(t, 1e140);
+    const double a = t + PHF_ERFCX_K, b = fma(2.0, t, 1.0);
+    const double r = rcp(a * b);
+    const double q = (t - PHF_ERFCX_K) * (r * b);
+    double xp[5];
+    xp[0] = q;
+    xp[1] = q * q;
+    xp[2] = xp[1] * xp[1];
+    xp[3] = xp[2] * xp[2];
+    xp[4] = xp[3] * xp[3];
+    const double P = poly<0, 22>(T + PHF_FM_KERFCXP, xp);
+    return P * (r * a);
+}
+
+// ---- log Phi(z), z <= 0: log(erfcx(|z|/sqrt2)/2) - z^2/2 (scipy.special.log_ndtr's z < -1 branch, accurate
+//      on all of z <= 0 because the value never comes near zero there) -------------------------------
+PHF_FM double log_ndtr_nonpos(const double *T, double z)
+{
+    const double t = fabs(z) * T[PHF_FM_KMISC + 2];
+    return log_pos(T, 0.5 * erfcx_nonneg(T, t)) - t * t;
+}
+
+// ---- sin and cos of 2 pi b / 2^32 ---------------------------------------------------------------
+PHF_FM void sincos_turn32(const double *T, uint32_t b, double &sn, double &cs)
+{
+    const double kScale = T[PHF_FM_KMISC + 1];  // pi / 2^31
+    const uint32_t bb = b + 0x20000000u;           // nearest multiple of a quarter turn
+    const uint32_t quad = bb >> 30;
+    const int32_t rem = (int32_t)(bb & 0x3fffffffu) - 0x20000000;  // [-2^29, 2^29)
+    const double r = (double)rem * kScale;                          // |r| <= pi/4
+    double xp[3];
+    xp[0] = r * r;
+    xp[1] = xp[0] * xp[0];
+    xp[2] = xp[1] * xp[1];
+    const double S = poly<0, 5>(T + PHF_FM_KSINS, xp);
+    const double C = poly<0, 5>(T + PHF_FM_KCOSC, xp);
+    const double s0 = fma(r * xp[0], S, r);
+    const double c0 = fma(xp[1], C, fma(-0.5, xp[0], 1.0));
+    // rotate by quad quarter turns
+    const bool swap = quad & 1u;
+    double s1 = swap ? c0 : s0;
+    double c1 = swap ? s0 : c0;
+    sn = (quad & 2u) ? -s1 : s1;
+    cs = ((quad + 1u) & 2u) ? -c1 : c1;
+}
+
+// ---- 10^x as exp(x ln 10) with a double-double ln 10 (model 1's 1/IC50) -----------------------------
+PHF_FM double exp10_clamped(const double *T, double x)
+{
+    const double kLn10Hi = T[PHF_FM_KMISC + 3], kLn10Lo = T[PHF_FM_KMISC + 4];
+    const double hi = x * kLn10Hi;
+    const double lo = fma(x, kLn10Lo, fma(x, kLn10Hi, -hi));
+    const double e = exp_clamped(T, hi);
+    return fma(e, lo, e);
+}
+
+}  // namespace fm
+}  // namespace phf

@@ -9,20 +9,6 @@
 
 namespace phf {
 
-template <int G>
-PHF_DI unsigned group_mask()
-{
-    return G == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16u));
-}
-
-template <int G>
-PHF_DI double group_sum(double v, unsigned mask)
-{
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
-    return v;
-}
-
 // Per-lane constants of the Gamma hyper-priors on theta[[0,1,2,3,-1]] (PyHillFit.py:187, 301, 363-364).
 struct LanePrior {
     double loc, shape_m1, inv_scale;  // zero on lanes that carry no hyper-prior
@@ -73,7 +59,7 @@ PHF_DI HierPoint load_point(const phf_hier_point *p)
 // log_target_distribution for the theta whose entry j sits on lane j of the group.  All lanes of the group
 // must call it; the result is uniform across the group.
 template <int G>
-PHF_DI double hier_log_target(double th_j, int gl, int dim, const LanePrior &lp, const HierPoint &pt0,
+PHF_DI double hier_log_target(const double *T, double th_j, int gl, int dim, const LanePrior &lp, const HierPoint &pt0,
                               const phf_hier_point *__restrict__ pts, int npts, unsigned mask)
 {
     // ---- support (PyHillFit.py:176-183) ----
@@ -123,7 +109,7 @@ PHF_DI double hier_log_target(double th_j, int gl, int dim, const LanePrior &lp,
         const double hill_e = __shfl_sync(mask, th_j, 5 + 2 * e, G);
         double lic_hi, lic_lo;
         ln_ic50(pic50_e, lic_hi, lic_lo);
-        const double x = hill_ratio_pow(P.lnc_hi, P.lnc_lo, lic_hi, lic_lo, hill_e);
+        const double x = hill_ratio_pow(T, P.lnc_hi, P.lnc_lo, lic_hi, lic_lo, hill_e);
         const double p = hill_response(x);
         const double r = P.y - p;
         // st.norm.cdf(100,p,sigma) - st.norm.cdf(0,p,sigma) with Phi(a) = erfc(-a/sqrt2)/2
@@ -147,6 +133,7 @@ __global__ void __launch_bounds__(128) hier_log_target_batch_kernel(int64_t n, c
                                                                     phf_hier_priors pr, double *__restrict__ out)
 {
     constexpr int G = 32;
+    PHF_STAGE_FASTMATH_TABLE(T);
     const int gl = threadIdx.x & (G - 1);
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     if (i >= n) return;  // whole warp exits together
@@ -156,7 +143,7 @@ __global__ void __launch_bounds__(128) hier_log_target_batch_kernel(int64_t n, c
     const LanePrior lp = lane_prior(gl, dim, pr);
     const phf_hier_point *pts = points + ds.point_begin;
     const HierPoint pt0 = load_point(pts + (gl < ds.n_points ? gl : 0));
-    const double lt = hier_log_target<G>(th_j, gl, dim, lp, pt0, pts, ds.n_points, 0xffffffffu);
+    const double lt = hier_log_target<G>(T, th_j, gl, dim, lp, pt0, pts, ds.n_points, 0xffffffffu);
     if (gl == 0) out[i] = lt;
 }
 
@@ -171,6 +158,7 @@ __global__ void __launch_bounds__(128) am_hier_init_kernel(int32_t dim, int64_t 
                                                            phf_hier_priors pr, double *__restrict__ state)
 {
     constexpr int G = 32;
+    PHF_STAGE_FASTMATH_TABLE(T);
     const int gl = threadIdx.x & (G - 1);
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     if (i >= n) return;
@@ -180,7 +168,7 @@ __global__ void __launch_bounds__(128) am_hier_init_kernel(int32_t dim, int64_t 
     const LanePrior lp = lane_prior(gl, dim, pr);
     const phf_hier_point *pts = points + ds.point_begin;
     const HierPoint pt0 = load_point(pts + (gl < ds.n_points ? gl : 0));
-    const double lt = hier_log_target<G>(th_j, gl, dim, lp, pt0, pts, ds.n_points, 0xffffffffu);
+    const double lt = hier_log_target<G>(T, th_j, gl, dim, lp, pt0, pts, ds.n_points, 0xffffffffu);
     double *s = state + i * nf;
     if (gl < dim) {
         s[gl] = th_j;
@@ -208,6 +196,7 @@ __global__ void __launch_bounds__(128) am_hier_kernel(phf_am_config cfg, int64_t
 {
     static_assert(DIM < G, "one lane per parameter row plus one for the log-target column");
     constexpr int NT = DIM * (DIM + 1) / 2, NF = PHF_STATE_SIZE(DIM);
+    PHF_STAGE_FASTMATH_TABLE(T);
     const int gl = threadIdx.x & (G - 1);
     const unsigned lane = threadIdx.x & 31u;
     const int64_t chain = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -259,7 +248,7 @@ __global__ void __launch_bounds__(128) am_hier_kernel(phf_am_config cfg, int64_t
         {
             const Philox4 r = philox_call(cfg.seed, chain_id, t, call);
             double z0, z1;
-            box_muller(hi_words ? r.w[2] : r.w[0], hi_words ? r.w[3] : r.w[1], z0, z1);
+            box_muller(T, hi_words ? r.w[2] : r.w[0], hi_words ? r.w[3] : r.w[1], z0, z1);
             z_j = (gl & 1) ? z1 : z0;
             u = __shfl_sync(mask, uniform53(r.w[0], r.w[1]), 0, G);  // lane 0 made call 0
         }
@@ -286,7 +275,7 @@ __global__ void __launch_bounds__(128) am_hier_kernel(phf_am_config cfg, int64_t
         }
 
         // ---- target, accept (PyHillFit.py:486-493) ----
-        const double lt_star = hier_log_target<G>(star_j, gl, DIM, lp, pt0, pts, npts, mask);
+        const double lt_star = hier_log_target<G>(T, star_j, gl, DIM, lp, pt0, pts, npts, mask);
         const bool accepted = log(u) < lt_star - lt;
         if (accepted) {
             th_j = star_j;

@@ -5,7 +5,19 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include "phf_fastmath.cuh"
+
 #define PHF_DI __device__ __forceinline__
+// every kernel that uses the fast-math functions starts with this (all threads reach it)
+#if PHF_FM_TABLE_MODE == 1
+#define PHF_STAGE_FASTMATH_TABLE(T)                                   \
+    __shared__ __align__(16) double T##_smem[PHF_FM_TABLE_SIZE];      \
+    phf::fm::stage_table(T##_smem);                                   \
+    __syncthreads();                                                  \
+    const double *const T = T##_smem
+#else
+#define PHF_STAGE_FASTMATH_TABLE(T) const double *const T = phf::fm::kFmTable
+#endif
 
 namespace phf {
 
@@ -20,6 +32,22 @@ constexpr double kSigmaScale = (6.0 - 1e-3) / (5.0 - 1.0);  // sigma_scale
 constexpr double kLn10Hi = 2.302585092994045901e+00;        // ln 10 rounded to double
 constexpr double kLn10Lo = -2.170756223382249351e-16;       // ln 10 - kLn10Hi
 constexpr double kSqrtHalf = 7.071067811865475244e-01;
+
+// ---- sub-warp lane groups: G consecutive lanes (G = 1, 2, 4, 8, 16 or 32) cooperate on one chain ----
+template <int G>
+PHF_DI unsigned group_mask()
+{
+    return G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (threadIdx.x & 31u & ~(unsigned)(G - 1)));
+}
+
+// butterfly sum: every lane of the group ends with the same bits (fp addition is commutative)
+template <int G>
+PHF_DI double group_sum(double v, unsigned mask)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
+    return v;
+}
 
 // ---- Philox4x32-10 (Salmon et al. 2011); stream contract in oracle/hill_oracle.py ----
 struct Philox4 {
@@ -56,13 +84,13 @@ PHF_DI double uniform53(uint32_t w0, uint32_t w1)
     return fma((double)v, 0x1p-53, 0x1p-54);
 }
 
-// two standard normals from two 32-bit words
-PHF_DI void box_muller(uint32_t a, uint32_t b, double &z0, double &z1)
+// two standard normals from two 32-bit words: r = sqrt(-2 ln((a+1) 2^-32)), angle = 2 pi b / 2^32
+PHF_DI void box_muller(const double *T, uint32_t a, uint32_t b, double &z0, double &z1)
 {
     const double u1 = fma((double)a, 0x1p-32, 0x1p-32);  // (a+1) 2^-32 in (0,1]
-    const double r = sqrt(-2.0 * log(u1));
+    const double r = fm::sqrt_nonneg(-2.0 * fm::log_pos(T, u1));
     double s, c;
-    sincospi((double)b * 0x1p-31, &s, &c);
+    fm::sincos_turn32(T, b, s, c);
     z0 = r * c;
     z1 = r * s;
 }
@@ -70,18 +98,7 @@ PHF_DI void box_muller(uint32_t a, uint32_t b, double &z0, double &z1)
 // log Phi(z) for z <= 0: scipy.special.log_ndtr's x < -1 branch, log(erfcx(-z/sqrt2)/2) - z^2/2, which is
 // also accurate on [-1, 0] (the value there is in [-1.85, -0.69], no cancellation).  Call sites only ever
 // pass z = (0-p)/sigma or (p-100)/sigma with p in [0,100] (python/doseresponse.py:218-219,244-245).
-PHF_DI double log_ndtr_nonpos(double z)
-{
-    const double t = fabs(z) * kSqrtHalf;
-    return log(0.5 * erfcx(t)) - t * t;
-}
-
-// general log Phi (only used by the batch API's generality tests)
-PHF_DI double log_ndtr(double z)
-{
-    if (z <= 0.0) return log_ndtr_nonpos(z);
-    return log1p(-0.5 * erfc(z * kSqrtHalf));
-}
+PHF_DI double log_ndtr_nonpos(const double *T, double z) { return fm::log_ndtr_nonpos(T, z); }
 
 // Phi(a): scipy.special.ndtr (cephes ndtr.c) as called by st.norm.cdf at python/PyHillFit.py:124
 PHF_DI double ndtr(double a)
@@ -107,14 +124,14 @@ PHF_DI void ln_ic50(double pic50, double &hi, double &lo)
 
 // (dose/IC50)^hill = exp(hill * (ln dose - ln IC50)) -- python/doseresponse.py:84-85.
 // 0^0 = inf^0 = 1 as numpy's power does.
-PHF_DI double hill_ratio_pow(double lnc_hi, double lnc_lo, double lic_hi, double lic_lo, double hill)
+PHF_DI double hill_ratio_pow(const double *T, double lnc_hi, double lnc_lo, double lic_hi, double lic_lo, double hill)
 {
     const double L = (lnc_hi - lic_hi) + (lnc_lo - lic_lo);
-    const double x = exp(hill * L);
+    const double x = fm::exp_clamped(T, hill * L);  // saturates at e^+-700, where the response is 100 / 0 to the last bit
     return hill == 0.0 ? 1.0 : x;
 }
 
 // predicted response 100 (1 - 1/(1 + x)) -- python/doseresponse.py:85
-PHF_DI double hill_response(double x) { return 100.0 * (1.0 - 1.0 / (1.0 + x)); }
+PHF_DI double hill_response(double x) { return 100.0 * (1.0 - fm::rcp(1.0 + x)); }
 
 }  // namespace phf

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(128) log_target_batch_kernel(int64_t n, const 
                                                                double *__restrict__ loglik_t1)
 {
     constexpr int D = SingleDims<MODEL>::D;
+    PHF_STAGE_FASTMATH_TABLE(T);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double th[D];
@@ -24,7 +25,7 @@ __global__ void __launch_bounds__(128) log_target_batch_kernel(int64_t n, const 
     for (int k = 0; k < D; ++k) th[k] = theta[i * D + k];
     const phf_dataset ds = datasets[dataset_id[i]];
     double lt, l1;
-    single_log_target<MODEL>(th, groups + ds.group_begin, ds.n_groups, ds.pi_bit, ds.n_other_total, temperature[i],
+    single_log_target<MODEL>(T, th, groups + ds.group_begin, ds.n_groups, ds.pi_bit, ds.n_other_total, temperature[i],
                              lt, l1);
     log_target[i] = lt;
     if (loglik_t1) loglik_t1[i] = l1;
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(128) am_single_init_kernel(int64_t n, const do
                                                              double *__restrict__ state)
 {
     constexpr int D = SingleDims<MODEL>::D, NT = SingleDims<MODEL>::NT, NF = SingleDims<MODEL>::NF;
+    PHF_STAGE_FASTMATH_TABLE(T);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double th[D];
@@ -50,7 +52,7 @@ __global__ void __launch_bounds__(128) am_single_init_kernel(int64_t n, const do
     for (int k = 0; k < D; ++k) th[k] = theta0[i * D + k];
     const phf_dataset ds = datasets[dataset_id[i]];
     double lt, l1;
-    single_log_target<MODEL>(th, groups + ds.group_begin, ds.n_groups, ds.pi_bit, ds.n_other_total, temperature[i],
+    single_log_target<MODEL>(T, th, groups + ds.group_begin, ds.n_groups, ds.pi_bit, ds.n_other_total, temperature[i],
                              lt, l1);
     double *s = state + i * NF;
 #pragma unroll
@@ -69,32 +71,66 @@ __global__ void __launch_bounds__(128) am_single_init_kernel(int64_t n, const do
 
 // ------------------------------------------------------------------------------------------------
 // fused adaptive Metropolis: python/PyHillFit.py:828-856 and python/PyHillTemp.py:87-123.
-// One thread per chain; theta, mean, covariance, loga, counters live in registers for all n_iters
-// iterations; the CTA's datasets are staged once in shared memory; HBM is touched only for the thinned
-// rows.  gamma_s = (s+1)^-0.6 depends on t only: lane L of each warp computes it for iteration t+L once
-// every 32 iterations and the warp reads it by shuffle.
+//
+// G consecutive lanes own one chain (G = 1, 2 or 4).  Every lane keeps the whole chain state (theta, mean,
+// covariance, loga, counters) in registers for all n_iters iterations and applies identical updates, so no
+// state is ever exchanged; what the lanes SPLIT is the expensive, independent work:
+//   * target:   lane gl evaluates dose group gl (exp, divide, erfcx+log when censored); lanes 0/1 take the two
+//               logarithms of sigma; two fp64 butterfly reductions bring the sums back to every lane;
+//   * draws:    the Philox/Box-Muller/log(u) work of an iteration depends on t only, so once every G
+//               iterations lane gl prepares the draws of iteration t+gl and the group reads them by shuffle;
+//   * gamma_s = (s+1)^-0.6 depends on t only: lane L of the warp computes it for iteration t+L once every 32
+//               iterations (all chains of a launch share t).
+// G = 1 is the throughput form (millions of chains, FP64-pipe bound); G = 4 shortens the dependent
+// instruction chain of one iteration ~3x for launches with too few chains to fill the SMs.
+// The CTA's datasets are staged once in shared memory; HBM is touched only for the thinned rows.
 // ------------------------------------------------------------------------------------------------
-template <int MODEL>
-__global__ void am_single_kernel(phf_am_config cfg, int64_t n, double *__restrict__ state,
-                                 const int32_t *__restrict__ dataset_id, const double *__restrict__ temperature,
-                                 const phf_dataset *__restrict__ datasets, const phf_dose_group *__restrict__ groups,
-                                 double *__restrict__ samples)
+template <int D>
+struct Draws {
+    double log_u;  // log of the accept uniform
+    double z[D];   // standard normals
+};
+
+template <int D>
+PHF_DI Draws<D> make_draws(const double *T, uint64_t seed, uint64_t chain_id, uint32_t t)
+{
+    Draws<D> dr;
+    const Philox4 r0 = philox_call(seed, chain_id, t, 0u);
+    dr.log_u = fm::log_pos(T, uniform53(r0.w[0], r0.w[1]));
+    box_muller(T, r0.w[2], r0.w[3], dr.z[0], dr.z[1]);
+    if (D == 3) {
+        const Philox4 r1 = philox_call(seed, chain_id, t, 1u);
+        double unused;
+        box_muller(T, r1.w[0], r1.w[1], dr.z[D - 1], unused);
+    }
+    return dr;
+}
+
+template <int MODEL, int G, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+    am_single_kernel(phf_am_config cfg, int64_t n, double *__restrict__ state, const int32_t *__restrict__ dataset_id,
+                     const double *__restrict__ temperature, const phf_dataset *__restrict__ datasets,
+                     const phf_dose_group *__restrict__ groups, double *__restrict__ samples)
 {
     constexpr int D = SingleDims<MODEL>::D, NT = SingleDims<MODEL>::NT, NF = SingleDims<MODEL>::NF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     phf_dose_group *sgroups = reinterpret_cast<phf_dose_group *>(smem_raw);
+    PHF_STAGE_FASTMATH_TABLE(T);
 
-    const int64_t first = (int64_t)blockIdx.x * blockDim.x;
-    const int64_t chain = first + threadIdx.x;
+    const int cta_chains = blockDim.x / G;
+    const int64_t first = (int64_t)blockIdx.x * cta_chains;
+    const int64_t chain = first + threadIdx.x / G;
+    const int gl = threadIdx.x & (G - 1);
     const bool active = chain < n;
     const int64_t c = active ? chain : n - 1;
     const unsigned lane = threadIdx.x & 31u;
+    const unsigned mask = group_mask<G>();
 
     // ---- stage this CTA's dose groups (chains are sorted by dataset, so the range is contiguous) ----
     const phf_dataset ds = datasets[dataset_id[c]];
     const phf_dose_group *grp = groups + ds.group_begin;
     if (cfg.stage_groups > 0) {
-        const int64_t last = min(first + (int64_t)blockDim.x, n) - 1;
+        const int64_t last = min(first + (int64_t)cta_chains, n) - 1;
         const phf_dataset d_lo = datasets[dataset_id[first]];
         const phf_dataset d_hi = datasets[dataset_id[last]];
         const int g_lo = d_lo.group_begin, g_hi = d_hi.group_begin + d_hi.n_groups;
@@ -115,6 +151,8 @@ __global__ void am_single_kernel(phf_am_config cfg, int64_t n, double *__restric
     const double pi_bit = ds.pi_bit, n_other_total = ds.n_other_total;
     const double temp = temperature[c];
     const uint64_t chain_id = cfg.chain_id_base + (uint64_t)c;
+    phf_dose_group g_own = {};
+    if (gl < ng) g_own = grp[gl];  // this lane's dose group stays in registers
 
     // ---- load chain state into registers ----
     double *sp = state + c * NF;
@@ -137,53 +175,57 @@ __global__ void am_single_kernel(phf_am_config cfg, int64_t n, double *__restric
     const uint32_t row_base = row + 1;
     double *out = samples ? samples + (size_t)c * cfg.rows_capacity * (D + 1) : nullptr;
     double gam_lane = 0.0;
+    Draws<D> mine;  // draws prepared by this lane (for iteration t + gl of the current block of G)
+    mine.log_u = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) mine.z[k] = 0.0;
 
     for (uint32_t it = 0; it < cfg.n_iters; ++it) {
         ++t;
         if ((it & 31u) == 0u) {
             const uint32_t tl = t + lane;
             // gamma_s = 1/(s+1)**0.6, s = t - adapt_when (PyHillFit.py:841-842, PyHillTemp.py:117)
-            gam_lane = tl > cfg.adapt_when ? 1.0 / pow((double)(tl - cfg.adapt_when) + 1.0, 0.6) : 0.0;
+            gam_lane = tl > cfg.adapt_when ? fm::exp_clamped(T, -0.6 * fm::log_pos(T, (double)(tl - cfg.adapt_when) + 1.0)) : 0.0;
         }
         const double gam = __shfl_sync(0xffffffffu, gam_lane, it & 31u);
 
         // ---- draws: accept uniform + D normals ----
-        double z[D + 1], u;
-        {
-            const Philox4 r0 = philox_call(cfg.seed, chain_id, t, 0u);
-            u = uniform53(r0.w[0], r0.w[1]);
-            box_muller(r0.w[2], r0.w[3], z[0], z[1]);
-            if (D == 3) {
-                const Philox4 r1 = philox_call(cfg.seed, chain_id, t, 1u);
-                double unused;
-                box_muller(r1.w[0], r1.w[1], z[2], unused);
-            }
+        Draws<D> dr;
+        if (G == 1) {
+            dr = make_draws<D>(T, cfg.seed, chain_id, t);
+        } else {
+            const int slot = (int)(it & (uint32_t)(G - 1));
+            if (slot == 0) mine = make_draws<D>(T, cfg.seed, chain_id, t + (uint32_t)gl);
+            dr.log_u = __shfl_sync(mask, mine.log_u, slot, G);
+#pragma unroll
+            for (int k = 0; k < D; ++k) dr.z[k] = __shfl_sync(mask, mine.z[k], slot, G);
         }
 
         // ---- proposal theta* = theta + e^{loga/2} chol(cov) z  (N(theta, e^loga cov): PyHillFit.py:831) ----
         double star[D];
         {
-            const double sc = exp(0.5 * loga);
-            const double r0 = rsqrt(cov[0]);
+            const double sc = fm::exp_clamped(T, 0.5 * loga);
+            const double r0 = fm::rsqrt(cov[0]);
             const double l00 = cov[0] * r0, l10 = cov[1] * r0;
             const double s11 = fma(-l10, l10, cov[2]);
-            const double r1 = rsqrt(s11);
+            const double r1 = fm::rsqrt(s11);
             const double l11 = s11 * r1;
-            star[0] = fma(sc, l00 * z[0], th[0]);
-            star[1] = fma(sc, fma(l10, z[0], l11 * z[1]), th[1]);
+            star[0] = fma(sc, l00 * dr.z[0], th[0]);
+            star[1] = fma(sc, fma(l10, dr.z[0], l11 * dr.z[1]), th[1]);
             if (D == 3) {
                 const double l20 = cov[3] * r0;
                 const double l21 = fma(-l20, l10, cov[4]) * r1;
                 const double s22 = fma(-l21, l21, fma(-l20, l20, cov[5]));
-                const double l22 = sqrt(s22);
-                star[D - 1] = fma(sc, fma(l20, z[0], fma(l21, z[1], l22 * z[2])), th[D - 1]);
+                const double l22 = s22 * fm::rsqrt(s22);
+                star[D - 1] = fma(sc, fma(l20, dr.z[0], fma(l21, dr.z[1], l22 * dr.z[D - 1])), th[D - 1]);
             }
         }
 
         // ---- target, accept (PyHillFit.py:833-838) ----
         double lt_star, l1_star;
-        single_log_target<MODEL>(star, grp, ng, pi_bit, n_other_total, temp, lt_star, l1_star);
-        const bool accepted = log(u) < lt_star - lt;
+        single_log_target_lanes<MODEL, G>(T, star, g_own, grp, ng, pi_bit, n_other_total, temp, gl, mask, lt_star,
+                                          l1_star);
+        const bool accepted = dr.log_u < lt_star - lt;
         if (accepted) {
 #pragma unroll
             for (int k = 0; k < D; ++k) th[k] = star[k];
@@ -218,15 +260,16 @@ __global__ void am_single_kernel(phf_am_config cfg, int64_t n, double *__restric
             ++row;
             if (out && active) {
                 double *o = out + (size_t)(row - row_base) * (D + 1);
+                // the G lanes of the chain write the row's D+1 columns between them
 #pragma unroll
-                for (int k = 0; k < D; ++k) o[k] = th[k];
-                o[D] = lt;
+                for (int k = 0; k <= D; ++k)
+                    if ((k & (G - 1)) == gl) o[k] = k < D ? th[k < D ? k : 0] : lt;
             }
             if (row >= cfg.burn_rows) l1_sum += l1;
         }
     }
 
-    if (active) {
+    if (active && gl == 0) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             sp[k] = th[k];
@@ -240,6 +283,23 @@ __global__ void am_single_kernel(phf_am_config cfg, int64_t n, double *__restric
         sp[2 * D + 2 + NT + 1] = l1_sum;
         sp[2 * D + 2 + NT + 2] = n_acc;
     }
+}
+
+template <int MODEL, int G, int MINB>
+static int launch_am_single(const phf_am_config &cfg, int64_t n, int block, size_t smem, double *state,
+                            const int32_t *dataset_id, const double *temperature, const phf_dataset *datasets,
+                            const phf_dose_group *groups, double *samples, cudaStream_t s)
+{
+    auto kern = am_single_kernel<MODEL, G, MINB>;
+    cudaError_t e;
+    if (smem > 48 * 1024 &&
+        (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)))
+        return set_cuda_error(e, "cudaFuncSetAttribute");
+    const int cta_chains = block / G;
+    const unsigned grid = (unsigned)((n + cta_chains - 1) / cta_chains);
+    kern<<<grid, block, smem, s>>>(cfg, n, state, dataset_id, temperature, datasets, groups, samples);
+    count_launch();
+    return check_launch("am_single_kernel");
 }
 
 }  // namespace phf
@@ -292,6 +352,16 @@ extern "C" int phf_am_single_init(int model, int64_t n_chains, const double *the
     return check_launch("am_single_init_kernel");
 }
 
+extern "C" int phf_am_single_lanes(int64_t n_chains)
+{
+    // G = 4 while every lane of every chain can be resident at once (768 threads/SM at <= 80 registers),
+    // then 2, then the one-thread-per-chain throughput form
+    const int64_t resident = (int64_t)sm_count() * 768;
+    if (n_chains * 4 <= resident) return 4;
+    if (n_chains * 2 <= resident) return 2;
+    return 1;
+}
+
 extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, double *state,
                                  const int32_t *dataset_id, const double *temperature, const phf_dataset *datasets,
                                  const phf_dose_group *groups, double *samples, void *stream)
@@ -307,27 +377,35 @@ extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, dou
         return set_error(PHF_EINVAL, "cfg.rows_capacity is smaller than the rows this call produces");
     if (n_chains == 0 || cfg->n_iters == 0) return PHF_OK;
 
+    int lanes = cfg->lanes_per_chain;
+    if (lanes == 0) lanes = phf_am_single_lanes(n_chains);
+    if (lanes != 1 && lanes != 2 && lanes != 4)
+        return set_error(PHF_EINVAL, "cfg.lanes_per_chain must be 0 (auto), 1, 2 or 4");
     int block = cfg->block_threads;
-    if (block <= 0) block = default_block_threads(n_chains);
-    if (block % 32 != 0 || block > 1024) return set_error(PHF_EINVAL, "cfg.block_threads must be a multiple of 32");
+    if (block <= 0) block = default_block_threads(n_chains * lanes);
+    if (block % 32 != 0 || block > 128)
+        return set_error(PHF_EINVAL, "cfg.block_threads must be a multiple of 32, at most 128");
     const size_t smem = cfg->stage_groups > 0 ? (size_t)cfg->stage_groups * sizeof(phf_dose_group) : 0;
     if (smem > 200 * 1024) return set_error(PHF_EINVAL, "cfg.stage_groups needs more than 200 KB of shared memory");
-    const unsigned grid = (unsigned)((n_chains + block - 1) / block);
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e;
-    if (cfg->model == 1) {
-        if (smem > 48 * 1024 &&
-            (e = cudaFuncSetAttribute(am_single_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)))
-            return set_cuda_error(e, "cudaFuncSetAttribute");
-        am_single_kernel<1><<<grid, block, smem, s>>>(*cfg, n_chains, state, dataset_id, temperature, datasets,
-                                                      groups, samples);
-    } else {
-        if (smem > 48 * 1024 &&
-            (e = cudaFuncSetAttribute(am_single_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)))
-            return set_cuda_error(e, "cudaFuncSetAttribute");
-        am_single_kernel<2><<<grid, block, smem, s>>>(*cfg, n_chains, state, dataset_id, temperature, datasets,
-                                                      groups, samples);
-    }
-    count_launch();
-    return check_launch("am_single_kernel");
+    const int minb = cfg->reserved > 0 ? cfg->reserved : (lanes == 1 ? 4 : 6);
+#define PHF_AM_CASE(M, G, MINB)                                                                                  \
+    if (cfg->model == M && lanes == G && minb == MINB)                                                                       \
+        return launch_am_single<M, G, MINB>(*cfg, n_chains, block, smem, state, dataset_id, temperature, datasets, \
+                                            groups, samples, s)
+    PHF_AM_CASE(1, 1, 4);
+    PHF_AM_CASE(1, 2, 6);
+    PHF_AM_CASE(1, 4, 6);
+    PHF_AM_CASE(2, 1, 4);
+    PHF_AM_CASE(2, 2, 6);
+    PHF_AM_CASE(2, 4, 6);
+    // experimental occupancy variants (cfg.reserved = min CTAs of 128 threads per SM)
+    PHF_AM_CASE(2, 1, 5);
+    PHF_AM_CASE(2, 1, 6);
+    PHF_AM_CASE(2, 2, 4);
+    PHF_AM_CASE(2, 4, 4);
+    PHF_AM_CASE(2, 4, 5);
+    PHF_AM_CASE(2, 4, 8);
+#undef PHF_AM_CASE
+    return set_error(PHF_EINVAL, "no kernel variant for this (model, lanes, occupancy hint)");
 }

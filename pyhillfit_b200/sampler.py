@@ -80,7 +80,8 @@ class _Base:
                              n_iters=int(n_iters), thinning=self.thinning, adapt_when=int(self.adapt_when),
                              burn_rows=int(self.burn_rows), rows_capacity=int(rows_capacity), seed=int(self.seed),
                              chain_id_base=int(self.chain_id_base), stage_groups=int(self.stage_groups),
-                             block_threads=int(self.block_threads))
+                             block_threads=int(self.block_threads), lanes_per_chain=int(getattr(self, "lanes", 0)),
+                             reserved=int(getattr(self, "occupancy_hint", 0)))
 
 
 class SingleLevelSampler(_Base):
@@ -92,10 +93,12 @@ class SingleLevelSampler(_Base):
     theta0       [n, d] start points
     variant      "fit" | "temp"  (initial covariance, adaptation start, mean reset)
     burn_rows    saved rows with index >= burn_rows accumulate the temperature-1 log-likelihood
+    lanes        lanes cooperating on one chain (1, 2, 4; 0 = the library's choice for this chain count)
     """
 
     def __init__(self, model, pack, dataset_id, temperature, theta0, variant="fit", cov0=None, adapt_when=None,
-                 seed=1, chain_id_base=0, thinning=5, burn_rows=NO_BURN, device=None, stage=True, block_threads=0):
+                 seed=1, chain_id_base=0, thinning=5, burn_rows=NO_BURN, device=None, stage=True, block_threads=0,
+                 lanes=0):
         if model not in (1, 2):
             raise ValueError("model must be 1 or 2")
         assert isinstance(pack, SinglePack)
@@ -120,14 +123,18 @@ class SingleLevelSampler(_Base):
         self.dataset_id = torch.from_numpy(ids).to(self.device)
         self.temperature = torch.from_numpy(temps).to(self.device)
         self.ds_dev, self.groups_dev = pack.device(self.device)
+        L = _lib.load()
+        if lanes not in (0, 1, 2, 4):
+            raise ValueError("lanes must be 0, 1, 2 or 4")
+        with torch.cuda.device(self.device):
+            self.lanes = int(lanes) if lanes else int(L.phf_am_single_lanes(n))
         self.block_threads = block_threads
         self.stage_groups = 0
         if stage and n > 0 and np.all(np.diff(ids) >= 0):
-            bt = block_threads if block_threads > 0 else self._default_block(n)
-            need = pack.stage_groups_needed(ids, bt)
+            bt = block_threads if block_threads > 0 else self._default_block(n * self.lanes)
+            need = pack.stage_groups_needed(ids, bt // self.lanes)   # a CTA of bt threads covers bt/lanes chains
             if need * 64 <= 96 * 1024:
                 self.stage_groups, self.block_threads = need, bt
-        L = _lib.load()
         with torch.cuda.device(self.device):
             _lib.check(L.phf_am_single_init(model, n, self._theta0.data_ptr(), self._cov0.data_ptr(),
                                             self.dataset_id.data_ptr(), self.temperature.data_ptr(),
