@@ -1,0 +1,223 @@
+"""Host-side logic that needs no GPU: the dataset packer (sufficient statistics reproduce the reference's per-point
+likelihood), chain sharding, the thermodynamic-integration tail, the ESS estimator, the on-disk formats, the output
+tree, and the command-line flags of the three scripts."""
+import os
+
+import numpy as np
+import pytest
+
+import hill_oracle as ho
+from _data import GOLD, Table
+
+
+@pytest.fixture(scope="module")
+def table():
+    return Table("crumb_data")
+
+
+# ---------------------------------------------------------------------------------------------
+# packing
+# ---------------------------------------------------------------------------------------------
+def _packed_loglik(model, g, pi_bit, n_other_total, th, t):
+    """numpy evaluation of the packed form documented in include/pyhillfit_b200.h (what the kernel computes)."""
+    from scipy.special import log_ndtr
+    pic50, hill, sigma = (th[0], 1.0, th[1]) if model == 1 else th
+    with np.errstate(all="ignore"):
+        x = (g["conc"] / 10 ** (6 - pic50)) ** hill
+        p = 100. * (1. - 1. / (1. + x))
+        e2 = np.sum(g["n_other"] * (g["ybar"] - p) ** 2 + g["ss"])
+        cens = np.sum(g["n0"] * log_ndtr((0 - p) / sigma)) + np.sum(g["n100"] * log_ndtr((p - 100) / sigma))
+    return t * (cens - pi_bit - n_other_total * np.log(sigma) - e2 / (2 * sigma ** 2))
+
+
+@pytest.mark.parametrize("model", [1, 2])
+def test_packed_sufficient_statistics_reproduce_the_per_point_likelihood(table, model):
+    from pyhillfit_b200.packing import pack_single_one
+    rng = np.random.default_rng(7)
+    for drug, channel in table.pairs()[::7] + [("Amitriptyline", "Kv4.3"), ("Bepridil", "hERG")]:
+        concs, y = table.concat(drug, channel)
+        g, pi_bit, n_other = pack_single_one(concs, y)
+        w0, w100, wo = ho.masks(y)
+        assert pi_bit == ho.compute_pi_bit_of_log_likelihood(wo)          # N_total, not n_uncensored
+        assert n_other == wo.sum() and g["n0"].sum() == w0.sum() and g["n100"].sum() == w100.sum()
+        assert len(g) == len(np.unique(concs))
+        for _ in range(5):
+            th = np.array([rng.uniform(3, 9), rng.uniform(0.3, 3), rng.uniform(1, 15)])
+            th = th if model == 2 else th[[0, 2]]
+            want = ho.log_data_likelihood(model, y, w0, w100, wo, concs, th, 0.7, pi_bit)
+            got = _packed_loglik(model, g, pi_bit, n_other, th, 0.7)
+            assert got == pytest.approx(want, rel=2e-13)
+
+
+def test_out_of_range_response_is_dropped_but_counted_in_pi_bit(table):
+    from pyhillfit_b200.packing import pack_single_one
+    concs, y = table.concat("Amitriptyline", "Kv4.3")          # holds the -2.6 response (data/crumb_data.csv:155)
+    assert (y < 0).sum() == 1
+    g, pi_bit, n_other = pack_single_one(concs, y)
+    assert g["n_other"].sum() + g["n0"].sum() + g["n100"].sum() == len(y) - 1
+    assert pi_bit == pytest.approx(0.5 * len(y) * np.log(2 * np.pi), rel=0, abs=0)
+    assert pi_bit == pytest.approx(17.45983213088878, rel=1e-15)   # SURVEY 8c known answer
+
+
+def test_pack_edge_cases():
+    from pyhillfit_b200.packing import HierPack, SinglePack, ln_hi_lo, pack_single_one
+    g, pb, no = pack_single_one([0.0, 1.0, 1.0], [0.0, 100.0, 50.0])
+    assert g["lnc_hi"][0] == -np.inf and g["lnc_lo"][0] == 0.0 and g["n0"][0] == 1
+    assert g["n100"][1] == 1 and g["n_other"][1] == 1 and g["ybar"][1] == 50.0 and g["ss"][1] == 0.0
+    hi, lo = ln_hi_lo(0.08)
+    assert hi == np.log(0.08) and abs(lo) < np.spacing(abs(hi))
+    with pytest.raises(ValueError):
+        pack_single_one([1.0, 2.0], [1.0])
+    with pytest.raises(ValueError):
+        pack_single_one([-1.0], [1.0])
+    empty = SinglePack([])
+    assert empty.n_datasets == 0 and len(empty.groups) == 0
+    ragged = SinglePack([([1.0], [10.0]), ([1.0, 2.0, 3.0, 4.0, 5.0], [1.0, 2.0, 3.0, 4.0, 5.0])])
+    assert list(ragged.datasets["n_groups"]) == [1, 5] and list(ragged.datasets["group_begin"]) == [0, 1]
+    ids = np.array([0, 0, 1, 1], dtype=np.int32)
+    assert ragged.stage_groups_needed(ids, 2) == 5 and ragged.stage_groups_needed(ids, 4) == 6
+    hp = HierPack([[np.array([[1.0, 5.0], [2.0, 9.0]]), np.array([[1.0, 6.0]])]])
+    assert list(hp.points["expt"]) == [0, 0, 1] and hp.datasets["n_expts"][0] == 2 and hp.datasets["n_points"][0] == 3
+
+
+# ---------------------------------------------------------------------------------------------
+# sharding / thermodynamic integration
+# ---------------------------------------------------------------------------------------------
+def test_shard_bounds_partition_and_balance():
+    from pyhillfit_b200.dist import shard_bounds
+    rng = np.random.default_rng(0)
+    w = rng.integers(2, 6, 26880).astype(float)
+    for ws in (1, 2, 3, 4, 8):
+        b = shard_bounds(w, ws)
+        assert b[0] == 0 and b[-1] == len(w) and len(b) == ws + 1 and np.all(np.diff(b) >= 0)
+        loads = np.array([w[b[r]:b[r + 1]].sum() for r in range(ws)])
+        assert loads.max() - loads.min() <= 2 * w.max()
+    assert list(shard_bounds([], 4)) == [0, 0, 0, 0, 0]
+    assert list(shard_bounds([1.0], 4))[-1] == 1
+
+
+def test_ti_tail_matches_the_reference_golden_bayes_factor():
+    """ladder, trapezium rule and B12 = exp(log p1 - log p2) on the reference chains' per-temperature means."""
+    from pyhillfit_b200 import ti
+    g = np.load(os.path.join(GOLD, "ref_chains.npz"))
+    temps = ti.temperature_ladder()
+    assert np.array_equal(temps, g["temps"]) and len(temps) == 41 and temps[1] == (1 / 40.) ** 3
+    lp1 = ti.log_py_from_means(temps, g["ladder_m1_ll1_mean"])
+    lp2 = ti.log_py_from_means(temps, g["ladder_m2_ll1_mean"])
+    assert lp1 == pytest.approx(float(g["log_py_m1"]), rel=1e-13)
+    assert lp2 == pytest.approx(float(g["log_py_m2"]), rel=1e-13)
+    assert np.exp(lp1 - lp2) == pytest.approx(float(g["B12"]), rel=1e-11)
+    assert lp1 == pytest.approx(ho.trapezium_rule(temps, g["ladder_m1_ll1_mean"]), rel=1e-14)
+    ids, tt = ti.build_chain_list(3, temps, 2)
+    assert len(ids) == 3 * 41 * 2 and np.all(np.diff(ids) >= 0) and tt[0] == tt[1] == 0.0 and tt[81] == 1.0
+
+
+def test_ess_estimator_on_ar1():
+    from pyhillfit_b200.ess import ess_geyer, ess_min
+    rng = np.random.default_rng(3)
+    n, rho = 200000, 0.9
+    x = np.empty(n)
+    x[0] = 0
+    e = rng.standard_normal(n)
+    for i in range(1, n):
+        x[i] = rho * x[i - 1] + e[i]
+    want = n * (1 - rho) / (1 + rho)
+    assert ess_geyer(x) == pytest.approx(want, rel=0.15)
+    assert ess_geyer(rng.standard_normal(5000)) > 4000
+    assert ess_min(np.stack([x[:5000], rng.standard_normal(5000)], 1)) < 1000
+    assert ess_geyer(np.ones(10)) == 10.0
+
+
+# ---------------------------------------------------------------------------------------------
+# on-disk formats and the output tree
+# ---------------------------------------------------------------------------------------------
+def test_chain_files_are_what_the_reference_consumers_read(tmp_path):
+    from pyhillfit_b200 import chainio
+    rng = np.random.default_rng(1)
+    chain = rng.standard_normal((7, 4))
+    f = str(tmp_path / "single.txt")
+    chainio.save_single_level_chain(f, chain, "Amiodarone", "hERG")
+    lines = open(f).read().split("\n")
+    assert lines[0] == "# Nonhierarchical MCMC output for Amiodarone + hERG: (Hill,pIC50,sigma,log-target)"
+    assert len(lines[1].split(" ")) == 4 and lines[1].split(" ")[0] == "%.18e" % chain[0, 0]
+    assert np.array_equal(np.loadtxt(f), chain)                            # plot_samples.py:50 etc.
+    assert np.array_equal(np.loadtxt(f, usecols=range(3)), chain[:, :3])   # compute_bayes_factors.py:14
+    f = str(tmp_path / "temp.txt")
+    chainio.save_tempered_chain(f, chain)
+    assert not open(f).read().startswith("#") and np.array_equal(np.loadtxt(f), chain)
+    hchain = rng.standard_normal((9, 12))
+    f = str(tmp_path / "hier.txt")
+    chainio.save_hierarchical_chain(f, hchain)
+    head = open(f).read().split("\n")[:2]
+    assert head[0] == "# Hill ~ log-logistic(alpha,beta), pIC50 ~ logistic(mu,s)"
+    assert head[1] == "# alpha, beta, mu, s, hill_1, pic50_1, hill_2, pic50_2, ..., hill_Ne, pic50_Ne, sigma"
+    assert np.array_equal(np.loadtxt(f), hchain)
+    f = str(tmp_path / "am.txt")
+    chainio.save_alpha_mu_samples(f, hchain, 2, 500, "D", "C", np.random.RandomState(0))
+    am = np.loadtxt(f)
+    assert am.shape == (500, 2) and open(f).readline() == "# 500 (alpha,mu) samples from hierarchical MCMC for D + C\n"
+    assert set(map(tuple, am)) <= set(map(tuple, hchain[2:, [0, 2]]))
+    bf = chainio.save_bayes_factor("D", "C", 3.25, str(tmp_path) + "/BFs/")
+    assert bf.endswith("BFs/D_C_B12.txt") and float(np.loadtxt(bf)) == 3.25
+    p = chainio.save_best_fit_params(str(tmp_path) + "/", "D", "C", 2, np.array([5.5, 1.0, 6.0]))
+    assert open(p).read().split("\n")[:2] == ["# CMA-ES best fit params", "# pIC50, Hill, sigma"]
+    assert np.array_equal(np.loadtxt(p), [5.5, 1.0, 6.0])
+
+
+def test_output_tree_and_loader(tmp_path, monkeypatch):
+    import pyhillfit_b200.doseresponse as dr
+    z = np.load(os.path.join(GOLD, "datasets.npz"))
+    monkeypatch.chdir(tmp_path)
+    dr.setup_from_arrays("crumb_data", z["crumb_data__drug"], z["crumb_data__channel"], z["crumb_data__experiment"],
+                         z["crumb_data__dose"], z["crumb_data__response"])
+    assert len(dr.drugs) == 30 and len(dr.channels) == 7 and dr.dir_name == "crumb_data"
+    ne, nums, ex = dr.load_crumb_data("Amiodarone", "hERG")
+    assert ne == 3 and list(nums) == [0, 1, 2] and [e.shape for e in ex] == [(4, 2)] * 3
+    assert list(ex[0][:, 1]) == [0, 12, 37.5, 66.5]
+    d, c, chain_file, images = dr.nonhierarchical_chain_file_and_figs_dir(2, "Quinidine", "KvLQT1/mink", 1)
+    assert (d, c) == ("Quinidine", "KvLQT1_mink")
+    assert chain_file == ("output/crumb_data/single-level/Quinidine/KvLQT1_mink/model_2/temperature_1/chain/"
+                          "Quinidine_KvLQT1_mink_model_2_temp_1_chain_single-level.txt")
+    assert os.path.isdir(images) and os.path.isdir(os.path.dirname(chain_file))
+    t = (np.arange(41.) / 40) ** 3
+    assert "temperature_1.5625000000000004e-05/" in dr.nonhierarchical_chain_file_and_figs_dir(1, "A", "B", t[1])[2]
+    assert "temperature_0.0/" in dr.nonhierarchical_chain_file_and_figs_dir(1, "A", "B", t[0])[2]
+    assert "temperature_1.0/" in dr.nonhierarchical_chain_file_and_figs_dir(1, "A", "B", t[40])[2]
+    out = dr.hierarchical_output_dirs_and_chain_file("Amiodarone", "hERG", 3)
+    assert out[5] == "output/crumb_data/hierarchical/Amiodarone/hERG/3_expts/chain/crumb_data_Amiodarone_hERG_hierarchical_chain.txt"
+    assert dr.alpha_mu_downsampling("Amiodarone", "hERG") == \
+        "output/crumb_data/hierarchical/alpha_mu_samples/Amiodarone_hERG_hill_pic50_samples.txt"
+    assert dr.n == 40 and dr.c == 3 and dr.trapezium_rule(np.array([0., 1.]), np.array([1., 3.])) == 2.0
+    mask = np.ones(12, dtype=bool)
+    assert dr.compute_pi_bit_of_log_likelihood(mask) == pytest.approx(11.027262398456072, rel=1e-15)
+    assert dr.pic50_to_ic50(6.0) == 1.0 and dr.dose_response_model(1.0, 1.0, 1.0) == 50.0
+
+
+def test_command_lines_keep_the_reference_flags():
+    from pyhillfit_b200 import PyHillFit, PyHillTemp, compute_bayes_factors
+    a = PyHillFit.build_parser().parse_args("--data-file d.csv -m 2 -a -i 1000 -t 5 -b 4 -c 3 -Ne 2 --num-APs 10 "
+                                            "--hierarchical -bfo -ppp".split())
+    assert (a.iterations, a.thinning, a.burn_in_fraction, a.num_cores, a.num_expts, a.num_APs) == (1000, 5, 4, 3, 2, 10)
+    assert a.all and a.hierarchical and a.best_fit_only and a.plot_parameter_paths and a.model == 2
+    d = PyHillFit.build_parser().parse_args("--data-file d.csv -m 1".split())
+    assert (d.iterations, d.thinning, d.burn_in_fraction, d.num_APs) == (500000, 5, 4, 500)
+    b = PyHillTemp.build_parser().parse_args("--data-file d.csv -m 1 -d 3 -c 5 -nc 8 --fix-hill".split())
+    assert (b.drug, b.channel, b.num_cores, b.fix_hill) == (3, 5, 8, True)      # -c is the CHANNEL here
+    c = compute_bayes_factors.build_parser().parse_args("--data-file d.csv -d 0 -c 1 -nc 2".split())
+    assert (c.drug, c.channel, c.num_cores) == (0, 1, 2)
+    with pytest.raises(SystemExit):
+        PyHillFit.build_parser().parse_args(["-m", "2"])                        # --data-file is required
+
+
+def test_initial_fit_minimises_the_reference_objective(table):
+    from pyhillfit_b200.initial_fit import best_fit, sum_of_square_diffs
+    concs, y = table.concat("Amiodarone", "hERG")
+    th, ss = best_fit(2, concs, y)
+    assert ss == pytest.approx(sum_of_square_diffs((th[0], th[1]), concs, y), rel=1e-12)
+    assert th[2] == pytest.approx(np.sqrt(ss / len(y)), rel=1e-12)              # PyHillFit.py:101-102, 729
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        trial = (th[0] + rng.normal(0, 0.3), abs(th[1] + rng.normal(0, 0.2)))
+        assert sum_of_square_diffs(trial, concs, y) >= ss - 1e-9
+    th1, _ = best_fit(1, concs, y)
+    assert th1.shape == (2,)
