@@ -286,13 +286,20 @@ static double hier_target_cb(const void *c, const double *theta, double *ll1)
     return hier_target((const hier_data *)c, theta);
 }
 
-/* lower Cholesky factor, row-major d x d; returns 0 on success */
+/* lower Cholesky factor, row-major d x d; returns 0 on success.
+ * Guarded pivots: the adapted covariance (1-g) C + g dd' is positive semi-definite but can be numerically singular
+ * (right after adaptation starts it is the empirical covariance of a path that has hardly moved); the reference
+ * draws through numpy's SVD factor (multivariate_normal), which tolerates that silently.  A pivot is therefore
+ * floored at PHF_PIVOT_FLOOR times its diagonal entry; the CUDA kernels apply the same floor. */
+#define PHF_PIVOT_FLOOR 1e-12
 static int cholesky(int d, const double *a, double *l)
 {
     memset(l, 0, sizeof(double) * d * d);
     for (int j = 0; j < d; ++j) {
         double s = a[j * d + j];
+        const double floor_j = PHF_PIVOT_FLOOR * a[j * d + j];
         for (int k = 0; k < j; ++k) s -= l[j * d + k] * l[j * d + k];
+        if (!(s > floor_j)) s = floor_j;
         if (!(s > 0)) return -1;
         double ljj = sqrt(s);
         l[j * d + j] = ljj;

@@ -277,6 +277,28 @@ def philox_draw(seed, chain, t, d):
 # PyHillFit.py:431-511 (variant "hier"), PyHillTemp.py:57-125 (variant "temp").
 # SURVEY.md section 3.5 tabulates the differences.
 # ----------------------------------------------------------------------------
+PIVOT_FLOOR = 1e-12
+
+
+def guarded_cholesky(a):
+    """Lower Cholesky factor with every pivot floored at PIVOT_FLOOR * a[j,j] (see oracle/hill_oracle.c: the
+    adapted covariance can be numerically singular; numpy's SVD-based multivariate_normal tolerates that)."""
+    a = np.asarray(a, dtype=float)
+    d = a.shape[0]
+    l = np.zeros((d, d))
+    for j in range(d):
+        s = a[j, j] - np.dot(l[j, :j], l[j, :j])
+        fl = PIVOT_FLOOR * a[j, j]
+        if not s > fl:
+            s = fl
+        if not s > 0:
+            raise np.linalg.LinAlgError("non-positive diagonal")
+        l[j, j] = math.sqrt(s)
+        for i in range(j + 1, d):
+            l[i, j] = (a[i, j] - np.dot(l[i, :j], l[j, :j])) / l[j, j]
+    return l
+
+
 def am_defaults(variant, theta0):
     """(cov0, adapt_when, reset_mean_at_adapt) for the three loops."""
     d = len(theta0)
@@ -317,7 +339,7 @@ def adaptive_metropolis(target, theta0, iterations, thinning, variant, rng="nump
             u = npr.rand()
         else:
             u, z = philox_draw(seed, chain_id, t, d)
-            theta_star = theta_cur + math.exp(0.5 * loga) * (np.linalg.cholesky(cov) @ z)
+            theta_star = theta_cur + math.exp(0.5 * loga) * (guarded_cholesky(cov) @ z)
             log_target_star = target(theta_star)
         if np.log(u) < log_target_star - log_target_cur:
             theta_cur = theta_star

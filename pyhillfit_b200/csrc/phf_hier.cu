@@ -260,9 +260,10 @@ __global__ void __launch_bounds__(128) am_hier_kernel(phf_am_config cfg, int64_t
             double v = crow[col];
 #pragma unroll
             for (int k = 0; k < col; ++k) v = fma(-lrow[k], __shfl_sync(mask, lrow[k], col, G), v);
-            const double piv = __shfl_sync(mask, v, col, G);
+            // lane `col` holds the pivot and its own diagonal entry crow[col]
+            const double piv = __shfl_sync(mask, guarded_pivot(v, crow[col]), col, G);
             const double rinv = rsqrt(piv);
-            lrow[col] = gl >= col ? v * rinv : 0.0;
+            lrow[col] = gl > col ? v * rinv : (gl == col ? piv * rinv : 0.0);
         }
 
         // ---- proposal theta* = theta + e^{loga/2} L z  (N(theta, e^loga cov): PyHillFit.py:485) ----

@@ -32,6 +32,16 @@ constexpr double kSigmaScale = (6.0 - 1e-3) / (5.0 - 1.0);  // sigma_scale
 constexpr double kLn10Hi = 2.302585092994045901e+00;        // ln 10 rounded to double
 constexpr double kLn10Lo = -2.170756223382249351e-16;       // ln 10 - kLn10Hi
 constexpr double kSqrtHalf = 7.071067811865475244e-01;
+// Cholesky pivots of the adapted covariance are floored at kPivotFloor * diagonal: (1-g) C + g dd' is positive
+// semi-definite but can be numerically singular (shortly after adaptation starts it is the empirical covariance
+// of a path that has hardly moved); the reference draws through numpy's SVD factor, which tolerates that.
+constexpr double kPivotFloor = 1e-12;
+
+__device__ __forceinline__ double guarded_pivot(double s, double diag)
+{
+    const double fl = kPivotFloor * diag;
+    return s > fl ? s : fl;  // NaN or non-positive diagonal stays non-positive / NaN -> proposal rejected
+}
 
 // ---- sub-warp lane groups: G consecutive lanes (G = 1, 2, 4, 8, 16 or 32) cooperate on one chain ----
 template <int G>

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(128, MINB)
             const double sc = fm::exp_clamped(T, 0.5 * loga);
             const double r0 = fm::rsqrt(cov[0]);
             const double l00 = cov[0] * r0, l10 = cov[1] * r0;
-            const double s11 = fma(-l10, l10, cov[2]);
+            const double s11 = guarded_pivot(fma(-l10, l10, cov[2]), cov[2]);
             const double r1 = fm::rsqrt(s11);
             const double l11 = s11 * r1;
             star[0] = fma(sc, l00 * dr.z[0], th[0]);
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(128, MINB)
             if (D == 3) {
                 const double l20 = cov[3] * r0;
                 const double l21 = fma(-l20, l10, cov[4]) * r1;
-                const double s22 = fma(-l21, l21, fma(-l20, l20, cov[5]));
+                const double s22 = guarded_pivot(fma(-l21, l21, fma(-l20, l20, cov[5])), cov[5]);
                 const double l22 = s22 * fm::rsqrt(s22);
                 star[D - 1] = fma(sc, fma(l20, dr.z[0], fma(l21, dr.z[1], l22 * dr.z[D - 1])), th[D - 1]);
             }

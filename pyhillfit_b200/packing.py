@@ -108,6 +108,47 @@ class SinglePack:
         self.datasets = np.array(ds, dtype=_lib.DATASET_DTYPE)
         self._dev = {}
 
+    @classmethod
+    def from_uniform(cls, concs, responses):
+        """Vectorised packer for many datasets that share one dose design (the synthetic scale-up, BASELINE
+        config 5): concs [N], responses [n_datasets, N].  Same statistics as pack_single_one, computed for all
+        datasets at once in extended precision."""
+        concs = np.asarray(concs, dtype=np.float64).ravel()
+        Y = np.atleast_2d(np.asarray(responses, dtype=np.float64))
+        if Y.shape[1] != len(concs):
+            raise ValueError("responses must be [n_datasets, len(concs)]")
+        n_ds = Y.shape[0]
+        uniq = []
+        for cval in concs:
+            if cval not in uniq:
+                uniq.append(cval)
+        D = len(uniq)
+        g = np.zeros((n_ds, D), dtype=_lib.DOSE_GROUP_DTYPE)
+        w0, w100, wo = masks(Y)
+        for k, cval in enumerate(uniq):
+            cols = np.nonzero(concs == cval)[0]
+            hi, lo = ln_hi_lo(cval)
+            g["lnc_hi"][:, k], g["lnc_lo"][:, k], g["conc"][:, k] = hi, lo, cval
+            yo = Y[:, cols].astype(_LD)
+            m = wo[:, cols]
+            cnt = m.sum(axis=1)
+            ybar = np.where(cnt > 0, (yo * m).sum(axis=1) / np.maximum(cnt, 1), 0)
+            yb = ybar.astype(np.float64).astype(_LD)      # centre on the rounded mean (see pack_single_one)
+            g["n_other"][:, k] = cnt
+            g["ybar"][:, k] = ybar.astype(np.float64)
+            g["ss"][:, k] = ((((yo - yb[:, None]) ** 2) * m).sum(axis=1)).astype(np.float64)
+            g["n0"][:, k] = w0[:, cols].sum(axis=1)
+            g["n100"][:, k] = w100[:, cols].sum(axis=1)
+        self = cls([])
+        self.groups = g.reshape(-1)
+        ds = np.zeros(n_ds, dtype=_lib.DATASET_DTYPE)
+        ds["group_begin"] = np.arange(n_ds, dtype=np.int64) * D
+        ds["n_groups"] = D
+        ds["pi_bit"] = 0.5 * len(concs) * np.log(2 * np.pi)
+        ds["n_other_total"] = wo.sum(axis=1)
+        self.datasets = ds
+        return self
+
     @property
     def n_datasets(self):
         return len(self.datasets)

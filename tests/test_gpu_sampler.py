@@ -156,11 +156,13 @@ def test_hier_trajectories_follow_oracle(table):
 
 
 def _quantile_check(samples, q_ref, sd_ref, ess_ref, n_sigma=5.0):
-    """GPU pooled quantiles vs reference quantiles, tolerance n_sigma * reference MCSE (quantile MCSE ~
-    1.6 sd / sqrt(ESS) for the 5/95 % points, 1.25 for the median; use the larger)."""
+    """GPU pooled quantiles vs reference quantiles.  MCSE of a quantile estimate = sqrt(p(1-p)/ESS_p) / density: for a
+    normal shape (2.11, 1.36, 1.25, 1.36, 2.11) x sd/sqrt(ESS) at the 5/25/50/75/95 % points; the ESS of a tail
+    indicator is below the ESS of the mean the fixture records, hence the extra factor 1.5."""
     q = np.percentile(samples, [5, 25, 50, 75, 95], axis=0)
-    tol = n_sigma * 1.7 * sd_ref / np.sqrt(ess_ref)
-    assert np.all(np.abs(q - q_ref) <= tol[None, :]), (q, q_ref, tol)
+    f = 1.5 * np.array([2.11, 1.36, 1.25, 1.36, 2.11])
+    tol = n_sigma * f[:, None] * (sd_ref / np.sqrt(ess_ref))[None, :]
+    assert np.all(np.abs(q - q_ref) <= tol), (q, q_ref, tol)
 
 
 @pytest.mark.parametrize("model", [1, 2])
