@@ -156,15 +156,22 @@ def _cpu_worker(args):
         return time.perf_counter() - t0
 
 
-def cpu_reference_rate(iters, warm=500, cores=None):
-    """chain-iterations/s of the reference algorithm (oracle port) with one chain per host core."""
+def cpu_reference_rate(iters, warm=500, cores=None, spread=False):
+    """chain-iterations/s of the reference algorithm (oracle port) with one chain per host core.
+    spread=False: every core runs Amiodarone/hERG model 2 (BASELINE configs[0]); spread=True: core k runs pair
+    17k mod 210 and models alternate, a sample of the config-2 workload."""
     from _data import Table
     from pyhillfit_b200.initial_fit import best_fit
     cores = cores or mp.cpu_count()
     table = Table("crumb_data")
-    concs, y = table.concat("Amiodarone", "hERG")
-    theta0, _ = best_fit(2, concs, y)
-    jobs = [(2, concs, y, theta0, warm, iters, 25 + k) for k in range(cores)]
+    pairs = table.pairs()
+    jobs = []
+    for k in range(cores):
+        drug, channel = pairs[(17 * k) % len(pairs)] if spread else ("Amiodarone", "hERG")
+        model = 1 + (k + 1) % 2 if spread else 2
+        concs, y = table.concat(drug, channel)
+        theta0, _ = best_fit(model, concs, y)
+        jobs.append((model, concs, y, theta0, warm, iters, 25 + k))
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
@@ -205,16 +212,16 @@ def run_reference_arm(args):
     rates = []
     cores = mp.cpu_count()
     for _ in range(args.warmup):
-        cpu_reference_rate(max(100, per_step // 10), warm=50)
+        cpu_reference_rate(max(100, per_step // 10), warm=50, spread=True)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r, cores, _ = cpu_reference_rate(per_step, warm=100)
+        r, cores, _ = cpu_reference_rate(per_step, warm=100, spread=True)
         rates.append(r)
     wall = time.perf_counter() - t0
     value = float(np.mean(rates))
     sample = ("%d chains (one per host core) x %d iterations per step of the PyHillFit single-level AM loop "
-              "(numpy/scipy restatement of python/PyHillFit.py:828-856 + doseresponse.py:187-248, numpy MT19937), "
-              "Amiodarone/hERG, model 2" % (cores, per_step))
+              "(numpy/scipy restatement of python/PyHillFit.py:828-856 + doseresponse.py:187-248, numpy MT19937); "
+              "core k runs Crumb pair 17k mod 210, models 1 and 2 alternate" % (cores, per_step))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -244,6 +251,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--no-stage", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -378,10 +386,17 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["am_single_kernel<2>"]
+        traffic = tr["dram_bytes_per_chain_iteration"] * n2 * K
+    except Exception:
+        pass
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                "traffic": None, "kernel": "am_single_kernel<2>", "launch_ms": kern_ms[2],
+                "traffic": traffic, "kernel": "am_single_kernel<2>", "launch_ms": kern_ms[2],
                 "flops_per_chain_iteration": wl[2]["flops"],
                 "peak_source": "phf_fp64_peak_probe (live DFMA microbenchmark; MEASURED_PEAKS.json has no FP64 entry)",
+                "algorithmic_bytes": n2 * K * (4 * 8.0 / thin),
                 "hbm": {"achieved_gbs": n2 * K * (4 * 8.0 / thin) / (kern_ms[2] * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
                         "algorithmic_bytes_per_chain_iteration": 4 * 8.0 / thin}}
@@ -395,6 +410,9 @@ def main():
                                   "%.1f s wall" % (cores, wall),
                         "c_port_value": rc,
                         "c_port_note": "same loop in plain C (oracle/hill_oracle.c, Philox RNG) on all cores"}
+    other = None
+    if world == 1 and not args.no_other_configs:
+        other = other_configs(torch, dev, pack)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -408,11 +426,83 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk, "ess_per_s": ess_per_s, "mean_acceptance": acc,
             "hbm_bytes_per_chain_iteration": bytes_iter, "flops_per_chain_iteration": flops_iter,
-            "kernel_ms": {"am_single_kernel<1>": kern_ms[1], "am_single_kernel<2>": kern_ms[2]}}
+            "kernel_ms": {"am_single_kernel<1>": kern_ms[1], "am_single_kernel<2>": kern_ms[2]},
+            "other_configs": other}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _timed(torch, fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return best * 1e-3
+
+
+def other_configs(torch, dev, pack):
+    """Device-timed throughput of BASELINE configs 3, 4 and one GPU's share of config 5 (context, not the headline;
+    each is one kernel launch timed alone, samples written, best of 3)."""
+    from _data import Table
+    from pyhillfit_b200 import synthetic, ti
+    from pyhillfit_b200.packing import HierPack, SinglePack
+    from pyhillfit_b200.sampler import HierarchicalSampler, SingleLevelSampler, hier_priors
+    out = {}
+    # config 4: PyHillTemp variant, 64 temperatures x 210 pairs x models 1, 2
+    temps = (np.arange(64.) / 63) ** 3
+    ids, tt = ti.build_chain_list(pack.n_datasets, temps, 1)
+    K = 5000
+    tot_t, tot_n = 0.0, 0
+    for model in (1, 2):
+        d = 2 if model == 1 else 3
+        s = SingleLevelSampler(model, pack, ids, tt, np.ones((len(ids), d)), variant="temp", seed=1, thinning=5,
+                               burn_rows=K // 20, device=dev)
+        buf = torch.empty((s.n, K // 5, d + 1), dtype=torch.float64, device=dev)
+        tot_t += _timed(torch, lambda: s.run(K, samples=buf))
+        tot_n += s.n
+    out["config4_ti_64_temperatures"] = {"chains": tot_n, "iters": K, "value": tot_n * K / tot_t, "unit": UNIT,
+                                         "note": "models 1 and 2 launched back to back"}
+    # config 5 share: 125 000 synthetic datasets x 4 chains = 500 000 chains, model 2, one thread per chain
+    concs, Y, _ = synthetic.generate(125000)
+    sp = SinglePack.from_uniform(concs, Y)
+    ids5 = np.repeat(np.arange(sp.n_datasets, dtype=np.int32), 4)
+    s5 = SingleLevelSampler(2, sp, ids5, 1.0, np.tile([6.0, 1.0, 6.0], (len(ids5), 1)), variant="fit", seed=9,
+                            thinning=5, device=dev)
+    K5 = 2000
+    buf5 = torch.empty((s5.n, K5 // 5, 4), dtype=torch.float64, device=dev)
+    t5 = _timed(torch, lambda: s5.run(K5, samples=buf5))
+    out["config5_synthetic_share"] = {"chains": s5.n, "iters": K5, "value": s5.n * K5 / t5, "unit": UNIT,
+                                      "lanes": s5.lanes, "note": "1/8 of 1M datasets x 4 chains (one GPU of eight)"}
+    del buf5, s5
+    # config 3: hierarchical, every Crumb pair x 256 chains (grouped by number of experiments)
+    table = Table("crumb_data")
+    pr, shapes, scales, locs = hier_priors()
+    pairs = table.pairs()
+    by_ne = {}
+    for ip, (dg, ch) in enumerate(pairs):
+        by_ne.setdefault(len(table.experiments(dg, ch)), []).append(ip)
+    K3 = 1000
+    tot_t, tot_n = 0.0, 0
+    for ne, idxs in sorted(by_ne.items()):
+        hp = HierPack([table.experiments(*pairs[i]) for i in idxs])
+        hid = np.repeat(np.arange(len(idxs), dtype=np.int32), 256)
+        th0 = np.tile(np.concatenate(([1.0, 4.0, 6.0, 0.3], np.tile([5.5, 1.0], ne), [8.0])), (len(hid), 1))
+        hs = HierarchicalSampler(hp, hid, th0, pr, seed=ne, thinning=5, device=dev)
+        hb = torch.empty((hs.n, K3 // 5, hs.d + 1), dtype=torch.float64, device=dev)
+        tot_t += _timed(torch, lambda: hs.run(K3, samples=hb))
+        tot_n += hs.n
+        del hb
+    out["config3_hierarchical"] = {"chains": tot_n, "iters": K3, "value": tot_n * K3 / tot_t, "unit": UNIT,
+                                   "note": "dim 11..17, four launches (Ne = 3, 4, 5, 6) back to back"}
+    return out
 
 
 def run_e2e(args, torch, dev, pack, wl, samplers, rank, world, dist):
