@@ -252,6 +252,9 @@ def main():
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--no-stage", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per chain (0: library default)")
+    ap.add_argument("--occupancy-hint", type=int, default=0, help="developer knob: min CTAs/SM variant")
+    ap.add_argument("--serial-models", action="store_true", help="run the two models back to back on one stream")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -285,7 +288,8 @@ def main():
         # disjoint Philox streams per rank: global chain id = rank * n_total + local index
         s = SingleLevelSampler(model, pack, w["ids"], 1.0, w["theta0"], variant="fit", seed=25,
                                chain_id_base=(rank * 2 + (model - 1)) * (1 << 32), thinning=thin, device=dev,
-                               stage=not args.no_stage, block_threads=args.block_threads)
+                               stage=not args.no_stage, block_threads=args.block_threads, lanes=args.lanes)
+        s.occupancy_hint = args.occupancy_hint
         samplers[model] = s
         buffers[model] = torch.empty((n, rows_per_step + 1, w["d"] + 1), dtype=torch.float64, device=dev)
         streams[model] = torch.cuda.Stream(device=dev)
@@ -296,6 +300,10 @@ def main():
     main_stream = torch.cuda.current_stream(dev)
 
     def step():
+        if args.serial_models:
+            for model in (2, 1):
+                samplers[model].run(K, samples=buffers[model])
+            return
         ev = torch.cuda.Event()
         ev.record(main_stream)
         for model in (1, 2):

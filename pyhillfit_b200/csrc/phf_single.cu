@@ -399,10 +399,18 @@ extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, dou
     PHF_AM_CASE(2, 1, 4);
     PHF_AM_CASE(2, 2, 6);
     PHF_AM_CASE(2, 4, 6);
-    // experimental occupancy variants (cfg.reserved = min CTAs of 128 threads per SM)
+    // other occupancy variants (cfg.reserved = min CTAs of 128 threads per SM; developer knob)
+    PHF_AM_CASE(1, 1, 5);
+    PHF_AM_CASE(1, 1, 6);
+    PHF_AM_CASE(1, 2, 4);
+    PHF_AM_CASE(1, 2, 5);
+    PHF_AM_CASE(1, 4, 4);
+    PHF_AM_CASE(1, 4, 5);
+    PHF_AM_CASE(1, 4, 8);
     PHF_AM_CASE(2, 1, 5);
     PHF_AM_CASE(2, 1, 6);
     PHF_AM_CASE(2, 2, 4);
+    PHF_AM_CASE(2, 2, 5);
     PHF_AM_CASE(2, 4, 4);
     PHF_AM_CASE(2, 4, 5);
     PHF_AM_CASE(2, 4, 8);
