@@ -288,7 +288,8 @@ def main():
         # disjoint Philox streams per rank: global chain id = rank * n_total + local index
         s = SingleLevelSampler(model, pack, w["ids"], 1.0, w["theta0"], variant="fit", seed=25,
                                chain_id_base=(rank * 2 + (model - 1)) * (1 << 32), thinning=thin, device=dev,
-                               stage=not args.no_stage, block_threads=args.block_threads, lanes=args.lanes)
+                               stage=not args.no_stage, block_threads=args.block_threads, lanes=args.lanes,
+                               co_resident_chains=0 if args.serial_models else len(wl[3 - model]["ids"]))
         s.occupancy_hint = args.occupancy_hint
         samplers[model] = s
         buffers[model] = torch.empty((n, rows_per_step + 1, w["d"] + 1), dtype=torch.float64, device=dev)

@@ -113,7 +113,8 @@ int phf_am_single_init(int model, int64_t n_chains, const double *theta0 /* [n,d
                        const double *temperature, const phf_dataset *datasets, const phf_dose_group *groups,
                        double *state /* [n, PHF_STATE_SIZE(d)] */, void *stream);
 
-/* lanes per chain the library picks for `n_chains` when cfg->lanes_per_chain == 0 (current device) */
+/* lanes per chain the library picks for `n_chains` resident chains when cfg->lanes_per_chain == 0 (current device);
+ * pass the total over all launches that run concurrently */
 int phf_am_single_lanes(int64_t n_chains);
 
 /*

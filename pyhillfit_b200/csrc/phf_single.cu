@@ -106,6 +106,100 @@ PHF_DI Draws<D> make_draws(const double *T, uint64_t seed, uint64_t chain_id, ui
     return dr;
 }
 
+// Registers of one chain (identical on the G lanes that own it).
+template <int MODEL>
+struct ChainRegs {
+    static constexpr int D = SingleDims<MODEL>::D, NT = SingleDims<MODEL>::NT;
+    double th[D], mean[D], cov[NT];
+    double lt, l1, loga, l1_sum, n_acc;
+};
+
+// Per-launch constants of one chain.
+struct ChainConst {
+    const phf_dose_group *grp;
+    int ng;
+    double pi_bit, n_other_total, temp;
+    uint32_t thinning, adapt_when, burn_rows, row_base;
+    int reset_mean;
+    double *out;  // this chain's rows of the samples buffer, or nullptr
+    bool active;
+};
+
+// One adaptive-Metropolis iteration (PyHillFit.py:829-848 / PyHillTemp.py:88-122) given its draws and gamma_s.
+template <int MODEL, int G>
+PHF_DI void am_step(const double *T, const ChainConst &cc, ChainRegs<MODEL> &s, const Draws<SingleDims<MODEL>::D> &dr,
+                    double gam, uint32_t t, int gl, unsigned mask, uint32_t &until_save, uint32_t &row)
+{
+    constexpr int D = SingleDims<MODEL>::D;
+    // ---- proposal theta* = theta + e^{loga/2} chol(cov) z  (N(theta, e^loga cov): PyHillFit.py:831) ----
+    double star[D];
+    {
+        const double sc = fm::exp_clamped(T, 0.5 * s.loga);
+        const double r0 = fm::rsqrt(s.cov[0]);
+        const double l00 = s.cov[0] * r0, l10 = s.cov[1] * r0;
+        const double s11 = guarded_pivot(fma(-l10, l10, s.cov[2]), s.cov[2]);
+        const double r1 = fm::rsqrt(s11);
+        const double l11 = s11 * r1;
+        star[0] = fma(sc, l00 * dr.z[0], s.th[0]);
+        star[1] = fma(sc, fma(l10, dr.z[0], l11 * dr.z[1]), s.th[1]);
+        if (D == 3) {
+            const double l20 = s.cov[3] * r0;
+            const double l21 = fma(-l20, l10, s.cov[4]) * r1;
+            const double s22 = guarded_pivot(fma(-l21, l21, fma(-l20, l20, s.cov[5])), s.cov[5]);
+            const double l22 = s22 * fm::rsqrt(s22);
+            star[D - 1] = fma(sc, fma(l20, dr.z[0], fma(l21, dr.z[1], l22 * dr.z[D - 1])), s.th[D - 1]);
+        }
+    }
+
+    // ---- target, accept (PyHillFit.py:833-838) ----
+    double lt_star, l1_star;
+    single_log_target_lanes<MODEL, G, true>(T, star, cc.grp, cc.ng, cc.pi_bit, cc.n_other_total, cc.temp, gl, mask,
+                                            lt_star, l1_star);
+    const bool accepted = dr.log_u < lt_star - s.lt;
+    if (accepted) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) s.th[k] = star[k];
+        s.lt = lt_star;
+        s.l1 = l1_star;
+        s.n_acc += 1.0;
+    }
+
+    // ---- adaptation (PyHillFit.py:840-846; PyHillTemp.py:114-122).  gam == 0 until t > adapt_when, and the update
+    //      with gam == 0 is the identity bit for bit, so there is no branch here ----
+    if (cc.reset_mean && t == cc.adapt_when) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) s.mean[k] = s.th[k];
+    }
+    {
+        const double omg = 1.0 - gam;
+        double dv[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) dv[k] = s.th[k] - s.mean[k];
+        int q = 0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j, ++q) s.cov[q] = fma(gam, dv[i] * dv[j], omg * s.cov[q]);
+#pragma unroll
+        for (int k = 0; k < D; ++k) s.mean[k] = fma(gam, s.th[k], omg * s.mean[k]);
+        s.loga = fma(gam, (accepted ? 1.0 : 0.0) - 0.25, s.loga);
+    }
+
+    // ---- thinned write-out (PyHillFit.py:847-848) + Sum loglik_t1 for thermodynamic integration ----
+    if (--until_save == 0u) {
+        until_save = cc.thinning;
+        ++row;
+        if (cc.out && cc.active) {
+            double *o = cc.out + (size_t)(row - cc.row_base) * (D + 1);
+            // the G lanes of the chain write the row's D+1 columns between them
+#pragma unroll
+            for (int k = 0; k <= D; ++k)
+                if ((k & (G - 1)) == gl) o[k] = k < D ? s.th[k < D ? k : 0] : s.lt;
+        }
+        if (row >= cc.burn_rows) s.l1_sum += s.l1;
+    }
+}
+
 template <int MODEL, int G, int MINB>
 __global__ void __launch_bounds__(128, MINB)
     am_single_kernel(phf_am_config cfg, int64_t n, double *__restrict__ state, const int32_t *__restrict__ dataset_id,
@@ -128,13 +222,14 @@ __global__ void __launch_bounds__(128, MINB)
 
     // ---- stage this CTA's dose groups (chains are sorted by dataset, so the range is contiguous) ----
     const phf_dataset ds = datasets[dataset_id[c]];
-    const phf_dose_group *grp = groups + ds.group_begin;
+    ChainConst cc;
+    cc.grp = ds.n_groups > 0 ? groups + ds.group_begin : groups;  // (an empty dataset still needs a readable address)
     if (cfg.stage_groups > 0) {
         const int64_t last = min(first + (int64_t)cta_chains, n) - 1;
         const phf_dataset d_lo = datasets[dataset_id[first]];
         const phf_dataset d_hi = datasets[dataset_id[last]];
         const int g_lo = d_lo.group_begin, g_hi = d_hi.group_begin + d_hi.n_groups;
-        const bool fits = (g_hi - g_lo) <= cfg.stage_groups && g_hi >= g_lo && ds.group_begin >= g_lo &&
+        const bool fits = (g_hi - g_lo) <= cfg.stage_groups && g_hi > g_lo && ds.group_begin >= g_lo &&
                           ds.group_begin + ds.n_groups <= g_hi;  // CTA-uniform except for unsorted input
         const int all_fit = __syncthreads_and(fits ? 1 : 0);
         if (all_fit) {
@@ -144,52 +239,61 @@ __global__ void __launch_bounds__(128, MINB)
             const int nvec = (g_hi - g_lo) * 4;
             for (int v = threadIdx.x; v < nvec; v += blockDim.x) dst[v] = __ldg(src + v);
             __syncthreads();
-            grp = sgroups + (ds.group_begin - g_lo);
+            cc.grp = sgroups + (ds.n_groups > 0 ? ds.group_begin - g_lo : 0);
         }
     }
-    const int ng = ds.n_groups;
-    const double pi_bit = ds.pi_bit, n_other_total = ds.n_other_total;
-    const double temp = temperature[c];
+    cc.ng = ds.n_groups;
+    cc.pi_bit = ds.pi_bit;
+    cc.n_other_total = ds.n_other_total;
+    cc.temp = temperature[c];
+    cc.thinning = cfg.thinning;
+    cc.adapt_when = cfg.adapt_when;
+    cc.burn_rows = cfg.burn_rows;
+    cc.reset_mean = cfg.reset_mean_at_adapt;
+    cc.active = active;
     const uint64_t chain_id = cfg.chain_id_base + (uint64_t)c;
-    phf_dose_group g_own = {};
-    if (gl < ng) g_own = grp[gl];  // this lane's dose group stays in registers
 
     // ---- load chain state into registers ----
     double *sp = state + c * NF;
-    double th[D], mean[D], cov[NT];
+    ChainRegs<MODEL> s;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        th[k] = sp[k];
-        mean[k] = sp[D + 2 + k];
+        s.th[k] = sp[k];
+        s.mean[k] = sp[D + 2 + k];
     }
-    double lt = sp[D], l1 = sp[D + 1];
+    s.lt = sp[D];
+    s.l1 = sp[D + 1];
 #pragma unroll
-    for (int k = 0; k < NT; ++k) cov[k] = sp[2 * D + 2 + k];
-    double loga = sp[2 * D + 2 + NT];
-    double l1_sum = sp[2 * D + 2 + NT + 1];
-    double n_acc = sp[2 * D + 2 + NT + 2];
+    for (int k = 0; k < NT; ++k) s.cov[k] = sp[2 * D + 2 + k];
+    s.loga = sp[2 * D + 2 + NT];
+    s.l1_sum = sp[2 * D + 2 + NT + 1];
+    s.n_acc = sp[2 * D + 2 + NT + 2];
 
     uint32_t t = cfg.t0;
     uint32_t until_save = cfg.thinning - (t % cfg.thinning);
     uint32_t row = t / cfg.thinning;
-    const uint32_t row_base = row + 1;
-    double *out = samples ? samples + (size_t)c * cfg.rows_capacity * (D + 1) : nullptr;
+    cc.row_base = row + 1;
+    cc.out = samples ? samples + (size_t)c * cfg.rows_capacity * (D + 1) : nullptr;
     double gam_lane = 0.0;
-    Draws<D> mine;  // draws prepared by this lane (for iteration t + gl of the current block of G)
+
+    // The draws of an iteration depend on t only: once every G iterations lane gl prepares the draws of iteration
+    // t + gl, and each iteration fetches its own by shuffle.  (Unrolling the G iterations so that the draw
+    // computation shares a basic block with an iteration was measured: faster alone, slower when the model-1 and
+    // model-2 kernels share an SM -- two unrolled bodies no longer fit the 32 KB instruction cache.)
+    Draws<D> mine;
     mine.log_u = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) mine.z[k] = 0.0;
-
     for (uint32_t it = 0; it < cfg.n_iters; ++it) {
         ++t;
         if ((it & 31u) == 0u) {
             const uint32_t tl = t + lane;
             // gamma_s = 1/(s+1)**0.6, s = t - adapt_when (PyHillFit.py:841-842, PyHillTemp.py:117)
-            gam_lane = tl > cfg.adapt_when ? fm::exp_clamped(T, -0.6 * fm::log_pos(T, (double)(tl - cfg.adapt_when) + 1.0)) : 0.0;
+            gam_lane = tl > cfg.adapt_when
+                           ? fm::exp_clamped(T, -0.6 * fm::log_pos(T, (double)(tl - cfg.adapt_when) + 1.0))
+                           : 0.0;
         }
         const double gam = __shfl_sync(0xffffffffu, gam_lane, it & 31u);
-
-        // ---- draws: accept uniform + D normals ----
         Draws<D> dr;
         if (G == 1) {
             dr = make_draws<D>(T, cfg.seed, chain_id, t);
@@ -200,88 +304,22 @@ __global__ void __launch_bounds__(128, MINB)
 #pragma unroll
             for (int k = 0; k < D; ++k) dr.z[k] = __shfl_sync(mask, mine.z[k], slot, G);
         }
-
-        // ---- proposal theta* = theta + e^{loga/2} chol(cov) z  (N(theta, e^loga cov): PyHillFit.py:831) ----
-        double star[D];
-        {
-            const double sc = fm::exp_clamped(T, 0.5 * loga);
-            const double r0 = fm::rsqrt(cov[0]);
-            const double l00 = cov[0] * r0, l10 = cov[1] * r0;
-            const double s11 = guarded_pivot(fma(-l10, l10, cov[2]), cov[2]);
-            const double r1 = fm::rsqrt(s11);
-            const double l11 = s11 * r1;
-            star[0] = fma(sc, l00 * dr.z[0], th[0]);
-            star[1] = fma(sc, fma(l10, dr.z[0], l11 * dr.z[1]), th[1]);
-            if (D == 3) {
-                const double l20 = cov[3] * r0;
-                const double l21 = fma(-l20, l10, cov[4]) * r1;
-                const double s22 = guarded_pivot(fma(-l21, l21, fma(-l20, l20, cov[5])), cov[5]);
-                const double l22 = s22 * fm::rsqrt(s22);
-                star[D - 1] = fma(sc, fma(l20, dr.z[0], fma(l21, dr.z[1], l22 * dr.z[D - 1])), th[D - 1]);
-            }
-        }
-
-        // ---- target, accept (PyHillFit.py:833-838) ----
-        double lt_star, l1_star;
-        single_log_target_lanes<MODEL, G>(T, star, g_own, grp, ng, pi_bit, n_other_total, temp, gl, mask, lt_star,
-                                          l1_star);
-        const bool accepted = dr.log_u < lt_star - lt;
-        if (accepted) {
-#pragma unroll
-            for (int k = 0; k < D; ++k) th[k] = star[k];
-            lt = lt_star;
-            l1 = l1_star;
-            n_acc += 1.0;
-        }
-
-        // ---- adaptation (PyHillFit.py:840-846; PyHillTemp.py:114-122) ----
-        if (cfg.reset_mean_at_adapt && t == cfg.adapt_when) {
-#pragma unroll
-            for (int k = 0; k < D; ++k) mean[k] = th[k];
-        }
-        if (t > cfg.adapt_when) {
-            const double omg = 1.0 - gam;
-            double dv[D];
-#pragma unroll
-            for (int k = 0; k < D; ++k) dv[k] = th[k] - mean[k];
-            int q = 0;
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j, ++q) cov[q] = fma(gam, dv[i] * dv[j], omg * cov[q]);
-#pragma unroll
-            for (int k = 0; k < D; ++k) mean[k] = fma(gam, th[k], omg * mean[k]);
-            loga = fma(gam, (accepted ? 1.0 : 0.0) - 0.25, loga);
-        }
-
-        // ---- thinned write-out (PyHillFit.py:847-848) + Sum loglik_t1 for thermodynamic integration ----
-        if (--until_save == 0u) {
-            until_save = cfg.thinning;
-            ++row;
-            if (out && active) {
-                double *o = out + (size_t)(row - row_base) * (D + 1);
-                // the G lanes of the chain write the row's D+1 columns between them
-#pragma unroll
-                for (int k = 0; k <= D; ++k)
-                    if ((k & (G - 1)) == gl) o[k] = k < D ? th[k < D ? k : 0] : lt;
-            }
-            if (row >= cfg.burn_rows) l1_sum += l1;
-        }
+        am_step<MODEL, G>(T, cc, s, dr, gam, t, gl, mask, until_save, row);
     }
 
     if (active && gl == 0) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            sp[k] = th[k];
-            sp[D + 2 + k] = mean[k];
+            sp[k] = s.th[k];
+            sp[D + 2 + k] = s.mean[k];
         }
-        sp[D] = lt;
-        sp[D + 1] = l1;
+        sp[D] = s.lt;
+        sp[D + 1] = s.l1;
 #pragma unroll
-        for (int k = 0; k < NT; ++k) sp[2 * D + 2 + k] = cov[k];
-        sp[2 * D + 2 + NT] = loga;
-        sp[2 * D + 2 + NT + 1] = l1_sum;
-        sp[2 * D + 2 + NT + 2] = n_acc;
+        for (int k = 0; k < NT; ++k) sp[2 * D + 2 + k] = s.cov[k];
+        sp[2 * D + 2 + NT] = s.loga;
+        sp[2 * D + 2 + NT + 1] = s.l1_sum;
+        sp[2 * D + 2 + NT + 2] = s.n_acc;
     }
 }
 
@@ -354,9 +392,11 @@ extern "C" int phf_am_single_init(int model, int64_t n_chains, const double *the
 
 extern "C" int phf_am_single_lanes(int64_t n_chains)
 {
-    // G = 4 while every lane of every chain can be resident at once (768 threads/SM at <= 80 registers),
-    // then 2, then the one-thread-per-chain throughput form
-    const int64_t resident = (int64_t)sm_count() * 768;
+    // Lanes are added while every lane of every chain can be resident at once at the kernels' full register budget
+    // (128 registers -> 512 threads per SM): measured on B200, a launch that does not fit in one wave, or that fits
+    // only with a tighter register cap (spills), is slower than the same launch with fewer lanes.  `n_chains`
+    // should count the chains of ALL launches that run concurrently (e.g. models 1 and 2 on two streams).
+    const int64_t resident = (int64_t)sm_count() * 512;
     if (n_chains * 4 <= resident) return 4;
     if (n_chains * 2 <= resident) return 2;
     return 1;
@@ -388,7 +428,7 @@ extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, dou
     const size_t smem = cfg->stage_groups > 0 ? (size_t)cfg->stage_groups * sizeof(phf_dose_group) : 0;
     if (smem > 200 * 1024) return set_error(PHF_EINVAL, "cfg.stage_groups needs more than 200 KB of shared memory");
     cudaStream_t s = (cudaStream_t)stream;
-    const int minb = cfg->reserved > 0 ? cfg->reserved : (lanes == 1 ? 4 : 6);
+    const int minb = cfg->reserved > 0 ? cfg->reserved : 4;
 #define PHF_AM_CASE(M, G, MINB)                                                                                  \
     if (cfg->model == M && lanes == G && minb == MINB)                                                                       \
         return launch_am_single<M, G, MINB>(*cfg, n_chains, block, smem, state, dataset_id, temperature, datasets, \

@@ -33,19 +33,45 @@ PHF_DI void dose_group_terms(const double *T, const phf_dose_group &Gd, double h
     }
 }
 
+// Sum of up to two censored terms w0 logPhi(z0) + w1 logPhi(z1) (a weight of 0 means "absent"; z stays finite).
+// VOTE = true (sampler kernels: every lane of the warp is alive and converged): the warp decides by vote whether
+// it needs the two-term path (both evaluations interleaved in one instruction stream), the one-term path or
+// none, so a warp whose chains share a censoring pattern never executes more evaluations than it needs.
+template <bool VOTE>
+PHF_DI double censored_pair(const double *T, double z0, double w0, double z1, double w1)
+{
+    const bool c0 = w0 > 0.0, c1 = w1 > 0.0;
+    bool two = c0 && c1, one = c0 || c1;
+    if (VOTE) {
+        two = __any_sync(0xffffffffu, two) != 0;
+        one = __any_sync(0xffffffffu, one) != 0;
+    }
+    double acc = 0.0;
+    if (two) {
+        acc = fma(w1, log_ndtr_nonpos(T, z1), w0 * log_ndtr_nonpos(T, z0));
+    } else if (one) {
+        acc = (c0 ? w0 : w1) * log_ndtr_nonpos(T, c0 ? z0 : z1);
+    }
+    return acc;
+}
+
 // Evaluate t * loglik + logprior and the temperature-1 loglik for one parameter vector with G cooperating
 // lanes (G = 1: a single thread).  Every lane of the group passes the same th; lane gl evaluates dose groups
 // gl, gl+G, ...; lanes 0 and 1 evaluate the two logarithms of sigma; sums are butterfly reductions, so every
 // lane returns the same bits.
-//   g_own    : dose group `gl` of the dataset, preloaded (ignored when gl >= ng)
-//   grp      : the dataset's dose groups (shared or global memory), used for groups >= G
+//
+// The first U = 4/G groups of a lane (all of them for the usual 4-dose design) are evaluated in ONE straight-line
+// block, predicated instead of looped: a lane issues in order, so independent chains (the two logarithms of sigma,
+// the U Hill curves) only overlap when the compiler can interleave them inside a basic block.  Censored terms are
+// then evaluated in pairs (censored_pair).  Further groups (ng > 4) take the general loop.
+//   grp      : the dataset's dose groups (shared or global memory)
+//   VOTE     : see censored_pair
 // Support (finite value) <=> pIC50 >= -3, 0 <= Hill <= 10, sigma > 1e-3; otherwise -inf like the reference:
 //   sigma <= 1e-3 -> likelihood -inf (doseresponse.py:212-214,238-240) and prior -inf (:306-308, log 0);
 //   pIC50 < -3 (:153-154) or Hill outside [0,10] (:181-182) -> prior -inf while the likelihood stays finite.
-template <int MODEL, int G>
-PHF_DI void single_log_target_lanes(const double *T, const double *th, const phf_dose_group &g_own,
-                                    const phf_dose_group *__restrict__ grp, int ng, double pi_bit,
-                                    double n_other_total, double temperature, int gl, unsigned mask,
+template <int MODEL, int G, bool VOTE>
+PHF_DI void single_log_target_lanes(const double *T, const double *th, const phf_dose_group *__restrict__ grp, int ng,
+                                    double pi_bit, double n_other_total, double temperature, int gl, unsigned mask,
                                     double &log_target, double &loglik_t1)
 {
     const double pic50 = th[0];
@@ -75,9 +101,44 @@ PHF_DI void single_log_target_lanes(const double *T, const double *th, const phf
     else
         inv_ic50 = fm::exp10_clamped(T, pic50 - 6.0);  // 1/IC50, IC50 = 10**(6-pIC50) (doseresponse.py:87-88)
 
+    constexpr int U = 4 / G;
     double e2 = 0.0, cens = 0.0;
-    if (gl < ng) dose_group_terms<MODEL>(T, g_own, hill, lic_hi, lic_lo, inv_ic50, inv_s, e2, cens);
-    for (int g = gl + G; g < ng; g += G) {
+    double zc[U], wc[U], pu[U];
+    bool both_kinds = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int g = gl + u * G;
+        const bool on = g < ng;
+        const phf_dose_group *Gp = grp + (on ? g : 0);
+        const double x = MODEL == 2 ? hill_ratio_pow(T, Gp->lnc_hi, Gp->lnc_lo, lic_hi, lic_lo, hill)
+                                    : Gp->conc * inv_ic50;
+        const double p = hill_response(x);
+        const double r = Gp->ybar - p;
+        const double gauss = fma(Gp->n_other * r, r, Gp->ss);
+        e2 += on ? gauss : 0.0;
+        const double n0 = Gp->n0, n100 = Gp->n100;
+        const bool has0 = on && n0 > 0.0, has100 = on && n100 > 0.0;
+        // st.norm.logcdf(0, p, sigma) / st.norm.logsf(100, p, sigma): doseresponse.py:218-219, 244-245
+        zc[u] = (has0 ? 0.0 - p : p - 100.0) * inv_s;
+        wc[u] = has0 ? n0 : (has100 ? n100 : 0.0);
+        pu[u] = p;
+        both_kinds = both_kinds || (has0 && has100);
+    }
+    if (U == 1) {
+        cens = censored_pair<VOTE>(T, zc[0], wc[0], zc[0], 0.0);
+    } else {
+#pragma unroll
+        for (int u = 0; u + 1 < U; u += 2) cens += censored_pair<VOTE>(T, zc[u], wc[u], zc[u + 1], wc[u + 1]);
+    }
+    if (both_kinds) {  // a dose carrying zeros AND hundreds (none in the Crumb table): its second term
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int g = gl + u * G;
+            if (g < ng && grp[g].n0 > 0.0 && grp[g].n100 > 0.0)
+                cens = fma(grp[g].n100, log_ndtr_nonpos(T, (pu[u] - 100.0) * inv_s), cens);
+        }
+    }
+    for (int g = gl + U * G; g < ng; g += G) {  // designs with more than four unique doses
         const phf_dose_group Gd = grp[g];
         dose_group_terms<MODEL>(T, Gd, hill, lic_hi, lic_lo, inv_ic50, inv_s, e2, cens);
     }
@@ -93,15 +154,14 @@ PHF_DI void single_log_target_lanes(const double *T, const double *th, const phf
     log_target = in_support ? lik + prior : -CUDART_INF;
 }
 
-// single-thread form used by the batch / init kernels
+// single-thread form used by the batch / init kernels (threads may have exited: no warp votes)
 template <int MODEL>
-PHF_DI void single_log_target(const double *T, const double *th, const phf_dose_group *__restrict__ grp, int ng, double pi_bit,
-                              double n_other_total, double temperature, double &log_target, double &loglik_t1)
+PHF_DI void single_log_target(const double *T, const double *th, const phf_dose_group *__restrict__ grp, int ng,
+                              double pi_bit, double n_other_total, double temperature, double &log_target,
+                              double &loglik_t1)
 {
-    phf_dose_group g0 = {};
-    if (ng > 0) g0 = grp[0];
-    single_log_target_lanes<MODEL, 1>(T, th, g0, grp, ng, pi_bit, n_other_total, temperature, 0, 0xffffffffu, log_target,
-                                      loglik_t1);
+    single_log_target_lanes<MODEL, 1, false>(T, th, grp, ng, pi_bit, n_other_total, temperature, 0, 0xffffffffu,
+                                             log_target, loglik_t1);
 }
 
 }  // namespace phf

@@ -94,11 +94,13 @@ class SingleLevelSampler(_Base):
     variant      "fit" | "temp"  (initial covariance, adaptation start, mean reset)
     burn_rows    saved rows with index >= burn_rows accumulate the temperature-1 log-likelihood
     lanes        lanes cooperating on one chain (1, 2, 4; 0 = the library's choice for this chain count)
+    co_resident_chains  chains of OTHER samplers whose launches run concurrently with this one (other streams);
+                 only used to choose `lanes`
     """
 
     def __init__(self, model, pack, dataset_id, temperature, theta0, variant="fit", cov0=None, adapt_when=None,
                  seed=1, chain_id_base=0, thinning=5, burn_rows=NO_BURN, device=None, stage=True, block_threads=0,
-                 lanes=0):
+                 lanes=0, co_resident_chains=0):
         if model not in (1, 2):
             raise ValueError("model must be 1 or 2")
         assert isinstance(pack, SinglePack)
@@ -127,7 +129,7 @@ class SingleLevelSampler(_Base):
         if lanes not in (0, 1, 2, 4):
             raise ValueError("lanes must be 0, 1, 2 or 4")
         with torch.cuda.device(self.device):
-            self.lanes = int(lanes) if lanes else int(L.phf_am_single_lanes(n))
+            self.lanes = int(lanes) if lanes else int(L.phf_am_single_lanes(n + int(co_resident_chains)))
         self.block_threads = block_threads
         self.stage_groups = 0
         if stage and n > 0 and np.all(np.diff(ids) >= 0):
