@@ -184,7 +184,12 @@ PHF_FM double exp_clamped(const double *T, double x)
     const double kLn2Hi = 0.693147182464599609375;    // 0x3fe62e4300000000: n * kLn2Hi is exact
     const double kLn2Lo = T[PHF_FM_KMISC + 0];         // ln 2 - kLn2Hi
     const double kMagic = 6755399441055744.0;         // 1.5 * 2^52
-    x = fmin(fmax(x, -700.0), 700.0);
+    // clamp on the high word (5 integer instructions; fmin/fmax cost 12 on sm_100a): |x| >= 700 or NaN -> +-700
+    {
+        const int hi = hi_word(x);
+        const bool big = (hi & 0x7fffffff) >= 0x4085e000;  // 0x4085e000'00000000 == 700.0
+        x = make_double(big ? ((hi & 0x80000000) | 0x4085e000) : hi, big ? 0 : lo_word(x));
+    }
     const double t = fma(x, kLog2eHi, kMagic);
     const int n = lo_word(t);
     const double nf = t - kMagic;

@@ -277,13 +277,13 @@ __global__ void __launch_bounds__(128, MINB)
     double gam_lane = 0.0;
 
     // The draws of an iteration depend on t only: once every G iterations lane gl prepares the draws of iteration
-    // t + gl, and each iteration fetches its own by shuffle.  (Unrolling the G iterations so that the draw
-    // computation shares a basic block with an iteration was measured: faster alone, slower when the model-1 and
-    // model-2 kernels share an SM -- two unrolled bodies no longer fit the 32 KB instruction cache.)
-    Draws<D> mine;
-    mine.log_u = 0.0;
-#pragma unroll
-    for (int k = 0; k < D; ++k) mine.z[k] = 0.0;
+    // t + gl and parks them in its shared-memory slot; each iteration then reads its slot (a broadcast load: 2
+    // instructions instead of 8 shuffles, and no registers held across iterations).  (Unrolling the G iterations so
+    // that the draw computation shares a basic block with an iteration was measured: faster alone, slower when the
+    // model-1 and model-2 kernels share an SM -- two unrolled bodies no longer fit the 32 KB instruction cache.)
+    double *const slots = reinterpret_cast<double *>(smem_raw + (size_t)cfg.stage_groups * sizeof(phf_dose_group));
+    double *const my_slot = slots + (size_t)threadIdx.x * (D + 1);
+    const double *const chain_slots = slots + (size_t)(threadIdx.x & ~(unsigned)(G - 1)) * (D + 1);
     for (uint32_t it = 0; it < cfg.n_iters; ++it) {
         ++t;
         if ((it & 31u) == 0u) {
@@ -299,10 +299,18 @@ __global__ void __launch_bounds__(128, MINB)
             dr = make_draws<D>(T, cfg.seed, chain_id, t);
         } else {
             const int slot = (int)(it & (uint32_t)(G - 1));
-            if (slot == 0) mine = make_draws<D>(T, cfg.seed, chain_id, t + (uint32_t)gl);
-            dr.log_u = __shfl_sync(mask, mine.log_u, slot, G);
+            if (slot == 0) {
+                const Draws<D> mine = make_draws<D>(T, cfg.seed, chain_id, t + (uint32_t)gl);
+                __syncwarp(mask);  // the group has finished reading the previous block's slots
+                my_slot[0] = mine.log_u;
 #pragma unroll
-            for (int k = 0; k < D; ++k) dr.z[k] = __shfl_sync(mask, mine.z[k], slot, G);
+                for (int k = 0; k < D; ++k) my_slot[1 + k] = mine.z[k];
+                __syncwarp(mask);
+            }
+            const double *src = chain_slots + slot * (D + 1);
+            dr.log_u = src[0];
+#pragma unroll
+            for (int k = 0; k < D; ++k) dr.z[k] = src[1 + k];
         }
         am_step<MODEL, G>(T, cc, s, dr, gam, t, gl, mask, until_save, row);
     }
@@ -425,7 +433,10 @@ extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, dou
     if (block <= 0) block = default_block_threads(n_chains * lanes);
     if (block % 32 != 0 || block > 128)
         return set_error(PHF_EINVAL, "cfg.block_threads must be a multiple of 32, at most 128");
-    const size_t smem = cfg->stage_groups > 0 ? (size_t)cfg->stage_groups * sizeof(phf_dose_group) : 0;
+    if (cfg->stage_groups < 0) return set_error(PHF_EINVAL, "cfg.stage_groups must be >= 0");
+    // staged dose groups + (lanes > 1) one draw slot of d+1 doubles per thread
+    const size_t smem = (size_t)cfg->stage_groups * sizeof(phf_dose_group) +
+                        (lanes > 1 ? (size_t)block * ((cfg->model == 1 ? 2 : 3) + 1) * sizeof(double) : 0);
     if (smem > 200 * 1024) return set_error(PHF_EINVAL, "cfg.stage_groups needs more than 200 KB of shared memory");
     cudaStream_t s = (cudaStream_t)stream;
     const int minb = cfg->reserved > 0 ? cfg->reserved : 4;
