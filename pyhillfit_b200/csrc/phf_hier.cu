@@ -68,11 +68,13 @@ PHF_DI double hier_log_target(const double *T, double th_j, int gl, int dim, con
     bad = __any_sync(mask, bad) != 0;
 
     // ---- one vector log for every entry, one for the Gamma hyper-priors ----
-    const double lth = log(th_j);
+    // (log_pos needs a positive argument: entries that may legitimately be <= 0 -- mu, pIC50_e -- never use theirs;
+    //  Hill_e == 0 is in support and the reference's log(0) = -inf is reproduced)
+    const double lth = th_j > 0.0 ? fm::log_pos(T, th_j) : -CUDART_INF;
     const double xm = th_j - lp.loc;
     double term = 0.0;
     {
-        const double lg = log(xm);
+        const double lg = fm::log_pos(T, xm > 0.0 ? xm : 1.0);
         if (lp.has_gamma) term = fma(lp.shape_m1, lg, -xm * lp.inv_scale);  // dr.log_gamma_prior (doseresponse.py:308)
     }
     const double alpha_l = __shfl_sync(mask, lth, 0, G);
@@ -87,18 +89,22 @@ PHF_DI double hier_log_target(const double *T, double th_j, int gl, int dim, con
     // ---- per-experiment terms: logistic on pIC50_e (even lane), log-logistic on Hill_e (odd lane) ----
     {
         const bool is_pic50 = (gl & 1) == 0;
-        const double zz = (th_j - mu) / s;                                   // PyHillFit.py:145
+        const double zz = (th_j - mu) * fm::rcp(s);                          // PyHillFit.py:145
         const double arg = is_pic50 ? -zz : beta * (lth - alpha_l);          // (x/alpha)**beta, PyHillFit.py:135
-        const double v = exp(arg);
-        const double l = log(1.0 + v);
+        // log(1 + e^arg): = arg to the last bit beyond 36; the reference's exp overflows to inf beyond ln(DBL_MAX)
+        // and the term becomes -inf (PyHillFit.py:135,146 -- an artefact that is part of its behaviour)
+        double l = fm::log_pos(T, 1.0 + fm::exp_clamped(T, arg));
+        l = arg > 36.0 ? arg : l;
+        l = arg > 709.782712893384 ? CUDART_INF : l;
         const double t_pic = -zz - s_l - 2.0 * l;                            // PyHillFit.py:146
         const double t_hill = beta_l - beta * alpha_l + (beta - 1.0) * lth - 2.0 * l;  // PyHillFit.py:135
         if (gl >= 4 && gl < dim - 1) term = is_pic50 ? t_pic : t_hill;
     }
 
     // ---- data likelihood, truncated-normal noise (PyHillFit.py:113-125): one point per lane per round ----
-    const double inv_s = 1.0 / sigma;
+    const double inv_s = fm::rcp(sigma);
     const double inv2s2 = 0.5 * inv_s * inv_s;
+    const double inv_s_rt2 = inv_s * kSqrtHalf;
     for (int base = 0; base < npts; base += G) {
         const int pi = base + gl;
         const bool has = pi < npts;
@@ -112,10 +118,15 @@ PHF_DI double hier_log_target(const double *T, double th_j, int gl, int dim, con
         const double x = hill_ratio_pow(T, P.lnc_hi, P.lnc_lo, lic_hi, lic_lo, hill_e);
         const double p = hill_response(x);
         const double r = P.y - p;
-        // st.norm.cdf(100,p,sigma) - st.norm.cdf(0,p,sigma) with Phi(a) = erfc(-a/sqrt2)/2
-        const double a = (100.0 - p) * inv_s, b = (0.0 - p) * inv_s;
-        const double dphi = 0.5 * (erfc(-a * kSqrtHalf) - erfc(-b * kSqrtHalf));
-        const double contrib = -(fma(r * r, inv2s2, log(dphi)) + sigma_l);
+        // st.norm.cdf(100,p,sigma) - st.norm.cdf(0,p,sigma) = 1 - (erfc(ta) + erfc(tb))/2 with ta = (100-p)/(sigma
+        // sqrt2) >= 0, tb = p/(sigma sqrt2) >= 0 (p is in [0,100]); erfc(t) = erfcx(t) e^{-t^2}.  The two
+        // evaluations are independent straight-line code, so they interleave.
+        const double ta = (100.0 - p) * inv_s_rt2, tb = p * inv_s_rt2;
+        const double qa = fm::erfcx_nonneg(T, ta) * fm::exp_clamped(T, -ta * ta);
+        const double qb = fm::erfcx_nonneg(T, tb) * fm::exp_clamped(T, -tb * tb);
+        const double dphi = 1.0 - 0.5 * (qa + qb);
+        const double ldphi = dphi > 0.0 ? fm::log_pos(T, dphi) : -CUDART_INF;
+        const double contrib = -(fma(r * r, inv2s2, ldphi) + sigma_l);
         if (has) term += contrib;
     }
     const double total = group_sum<G>(term, mask);
@@ -239,7 +250,9 @@ __global__ void __launch_bounds__(128) am_hier_kernel(phf_am_config cfg, int64_t
         ++t;
         if ((it & 31u) == 0u) {
             const uint32_t tl = t + lane;
-            gam_lane = tl > cfg.adapt_when ? 1.0 / pow((double)(tl - cfg.adapt_when) + 1.0, 0.6) : 0.0;  // PyHillFit.py:496-497
+            gam_lane = tl > cfg.adapt_when  // PyHillFit.py:496-497
+                           ? fm::exp_clamped(T, -0.6 * fm::log_pos(T, (double)(tl - cfg.adapt_when) + 1.0))
+                           : 0.0;
         }
         const double gam = __shfl_sync(0xffffffffu, gam_lane, it & 31u);
 
@@ -262,7 +275,7 @@ __global__ void __launch_bounds__(128) am_hier_kernel(phf_am_config cfg, int64_t
             for (int k = 0; k < col; ++k) v = fma(-lrow[k], __shfl_sync(mask, lrow[k], col, G), v);
             // lane `col` holds the pivot and its own diagonal entry crow[col]
             const double piv = __shfl_sync(mask, guarded_pivot(v, crow[col]), col, G);
-            const double rinv = rsqrt(piv);
+            const double rinv = fm::rsqrt(piv);
             lrow[col] = gl > col ? v * rinv : (gl == col ? piv * rinv : 0.0);
         }
 
@@ -272,12 +285,12 @@ __global__ void __launch_bounds__(128) am_hier_kernel(phf_am_config cfg, int64_t
             double acc = 0.0;
 #pragma unroll
             for (int k = 0; k < DIM; ++k) acc = fma(lrow[k], __shfl_sync(mask, z_j, k, G), acc);
-            star_j = fma(exp(0.5 * loga), acc, th_j);
+            star_j = fma(fm::exp_clamped(T, 0.5 * loga), acc, th_j);
         }
 
         // ---- target, accept (PyHillFit.py:486-493) ----
         const double lt_star = hier_log_target<G>(T, star_j, gl, DIM, lp, pt0, pts, npts, mask);
-        const bool accepted = log(u) < lt_star - lt;
+        const bool accepted = fm::log_pos(T, u) < lt_star - lt;
         if (accepted) {
             th_j = star_j;
             lt = lt_star;

@@ -119,7 +119,7 @@ class SingleLevelSampler(_Base):
         self._alloc_common(n, theta0, cov0, device)
         torch = self.torch
         ids = np.ascontiguousarray(dataset_id, dtype=np.int32).reshape(-1)
-        temps = np.ascontiguousarray(np.broadcast_to(np.asarray(temperature, dtype=np.float64), (n,)))
+        temps = np.array(np.broadcast_to(np.asarray(temperature, dtype=np.float64), (n,)))   # writable copy
         if ids.shape[0] != n or ids.min(initial=0) < 0 or ids.max(initial=0) >= pack.n_datasets:
             raise ValueError("dataset_id must be [n] with values in [0, n_datasets)")
         self.dataset_id = torch.from_numpy(ids).to(self.device)
@@ -271,8 +271,8 @@ def log_target_batch(model, pack, theta, dataset_id, temperature, device=None):
     d = 2 if model == 1 else 3
     th = torch.as_tensor(np.ascontiguousarray(theta, dtype=np.float64)).reshape(-1, d).to(device)
     n = th.shape[0]
-    ids = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(dataset_id, (n,)), dtype=np.int32)).to(device)
-    tt = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(np.asarray(temperature, dtype=np.float64), (n,)))).to(device)
+    ids = torch.as_tensor(np.array(np.broadcast_to(dataset_id, (n,)), dtype=np.int32)).to(device)
+    tt = torch.as_tensor(np.array(np.broadcast_to(np.asarray(temperature, dtype=np.float64), (n,)))).to(device)
     ds, groups = pack.device(device)
     out = torch.empty((2, n), dtype=torch.float64, device=device)
     with torch.cuda.device(device):
@@ -289,7 +289,7 @@ def hier_log_target_batch(pack, theta, dataset_id, priors, device=None):
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     th = torch.as_tensor(np.ascontiguousarray(theta, dtype=np.float64)).to(device)
     n, stride = th.shape
-    ids = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(dataset_id, (n,)), dtype=np.int32)).to(device)
+    ids = torch.as_tensor(np.array(np.broadcast_to(dataset_id, (n,)), dtype=np.int32)).to(device)
     ds, pts = pack.device(device)
     out = torch.empty(n, dtype=torch.float64, device=device)
     with torch.cuda.device(device):

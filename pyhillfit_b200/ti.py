@@ -36,9 +36,11 @@ def log_py_from_means(temps, means):
 
 
 def run_ti(datasets, models=(1, 2), temps=None, replicates=1, iterations=500000, thinning=5, burn_in_fraction=4,
-           seed=1, segment=50000, device=None, progress=None):
+           seed=1, segment=50000, device=None, progress=None, lanes=0):
     """datasets: list of (concs, responses).  Returns dict with log_py[model] -> [n_pairs], B12 [n_pairs],
-    means[model] -> [n_pairs, T] (averaged over replicates), acceptance[model] -> [n_pairs, T, R]."""
+    means[model] -> [n_pairs, T] (averaged over replicates), acceptance[model] -> [n_pairs, T, R].
+    Under torch.distributed (one process per GPU) the global chain list is sharded contiguously over the ranks and
+    every rank returns the full result; with a fixed `lanes` the result does not depend on the number of ranks."""
     import torch
     temps = temperature_ladder() if temps is None else np.asarray(temps, dtype=np.float64)
     ws, rank, local = phf_dist.world()
@@ -57,7 +59,7 @@ def run_ti(datasets, models=(1, 2), temps=None, replicates=1, iterations=500000,
         if hi > lo:
             s = SingleLevelSampler(model, pack, ids[lo:hi], tt[lo:hi], np.ones((hi - lo, d)), variant="temp",
                                    seed=seed, chain_id_base=base + lo, thinning=thinning, burn_rows=burn,
-                                   device=device)
+                                   device=device, lanes=lanes)
             done = 0
             while done < iterations:
                 k = min(segment, iterations - done)
