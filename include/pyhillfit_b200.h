@@ -176,6 +176,15 @@ int phf_am_single_run_host(const phf_am_config *cfg, int64_t n_chains, double *s
                            int32_t device);
 
 /* ------------------------------------------------------------------------------------------------
+ * Chain / sample files.  Replaces np.savetxt at python/PyHillFit.py:514-515, 524-525, 866-867 and
+ * python/PyHillTemp.py:169: writes `header` verbatim (may be NULL; include the '#' and the newline) and then
+ * n_rows x n_cols numbers as "%.18e", space separated, one row per line -- byte for byte what numpy writes --
+ * formatted on n_threads host threads (<= 0: all).  `data` is a HOST array with rows `row_stride` doubles apart.
+ * ---------------------------------------------------------------------------------------------- */
+int phf_write_rows_text_host(const char *path, const char *header, const double *data, int64_t n_rows, int32_t n_cols,
+                             int64_t row_stride, int32_t append, int32_t n_threads);
+
+/* ------------------------------------------------------------------------------------------------
  * Utilities
  * ---------------------------------------------------------------------------------------------- */
 int phf_version(void);

@@ -43,7 +43,7 @@ assert DOSE_GROUP_DTYPE.itemsize == 64 and DATASET_DTYPE.itemsize == 32
 assert HIER_POINT_DTYPE.itemsize == 32 and HIER_DATASET_DTYPE.itemsize == 16
 
 EXPORTS = ["phf_log_target_batch", "phf_am_single_init", "phf_am_single_run", "phf_am_single_lanes", "phf_hier_log_target_batch",
-           "phf_am_hier_init", "phf_am_hier_run", "phf_am_single_run_host", "phf_version", "phf_last_error",
+           "phf_am_hier_init", "phf_am_hier_run", "phf_am_single_run_host", "phf_write_rows_text_host", "phf_version", "phf_last_error",
            "phf_fp64_peak_probe", "phf_launch_count"]
 
 _lib = None
@@ -77,6 +77,8 @@ def load():
                                   C.POINTER(HierPriors), _p, _p]
     L.phf_am_single_run_host.argtypes = [C.POINTER(AmConfig), C.c_int64, _p, _p, _p, C.c_int32, _p, C.c_int32, _p,
                                          _p, C.c_int32, C.c_int32]
+    L.phf_write_rows_text_host.argtypes = [C.c_char_p, C.c_char_p, _p, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
+                                           C.c_int32]
     for name in EXPORTS:
         f = getattr(L, name)
         if f.restype is C.c_int and name not in ("phf_version",):
@@ -122,3 +124,19 @@ def fp64_peak_tflops(repeats=5):
     tf, sec = C.c_double(0), C.c_double(0)
     check(load().phf_fp64_peak_probe(repeats, C.byref(tf), C.byref(sec)), "phf_fp64_peak_probe")
     return tf.value, sec.value
+
+
+def write_rows_text(path, array, header=None, append=False, threads=0):
+    """np.savetxt(path, array) with an optional verbatim header, formatted by libphf_b200.so on all host cores
+    (byte-identical output; see phf_write_rows_text_host)."""
+    a = np.asarray(array, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)                      # numpy writes a 1-D array one value per line
+    if a.ndim != 2:
+        raise ValueError("expected a 1-D or 2-D array")
+    if a.strides[1] != 8 or a.strides[0] % 8 != 0 or a.strides[0] < 8 * a.shape[1]:
+        a = np.ascontiguousarray(a)
+    hdr = None if header is None else header.encode("utf-8")
+    check(load().phf_write_rows_text_host(os.fsencode(path), hdr, a.ctypes.data, a.shape[0], a.shape[1],
+                                          a.strides[0] // 8, int(bool(append)), int(threads)),
+          "phf_write_rows_text_host")

@@ -14,24 +14,23 @@ import os
 
 import numpy as np
 
+from . import _lib
+
 
 def save_single_level_chain(chain_file, chain, drug, channel):
-    with open(chain_file, 'w') as outfile:
-        # (the reference's header names the columns in the wrong order; kept verbatim)
-        outfile.write('# Nonhierarchical MCMC output for {} + {}: (Hill,pIC50,sigma,log-target)\n'.format(drug, channel))
-        np.savetxt(outfile, chain)
+    # (the reference's header names the columns in the wrong order; kept verbatim)
+    _lib.write_rows_text(chain_file, chain, header='# Nonhierarchical MCMC output for {} + {}: '
+                         '(Hill,pIC50,sigma,log-target)\n'.format(drug, channel))
 
 
 def save_tempered_chain(chain_file, chain):
-    np.savetxt(chain_file, chain)
+    _lib.write_rows_text(chain_file, chain)
 
 
 def save_hierarchical_chain(chain_file, chain):
-    with open(chain_file, 'w') as outfile:
-        outfile.write("# Hill ~ log-logistic(alpha,beta), pIC50 ~ logistic(mu,s)\n")
-        outfile.write("# alpha, beta, mu, s, hill_1, pic50_1, hill_2, pic50_2, ..., hill_Ne, pic50_Ne, sigma\n")
-    with open(chain_file, 'a') as outfile:
-        np.savetxt(outfile, chain)
+    _lib.write_rows_text(chain_file, chain,
+                         header="# Hill ~ log-logistic(alpha,beta), pIC50 ~ logistic(mu,s)\n"
+                                "# alpha, beta, mu, s, hill_1, pic50_1, hill_2, pic50_2, ..., hill_Ne, pic50_Ne, sigma\n")
 
 
 def save_alpha_mu_samples(samples_file, chain, burn, num_APs, drug, channel, rng=None):

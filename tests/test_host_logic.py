@@ -221,3 +221,29 @@ def test_initial_fit_minimises_the_reference_objective(table):
         assert sum_of_square_diffs(trial, concs, y) >= ss - 1e-9
     th1, _ = best_fit(1, concs, y)
     assert th1.shape == (2,)
+
+
+def test_native_text_writer_is_byte_identical_to_savetxt(tmp_path):
+    """phf_write_rows_text_host (all host cores) vs np.savetxt(fmt='%.18e'): same bytes, incl. signed zero,
+    infinities, nan, subnormals, 3-digit exponents, strided views, 1-D input, headers and append mode."""
+    from pyhillfit_b200 import _lib
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((30011, 4)) * np.exp(rng.uniform(-300, 300, (30011, 4)))
+    a[0, 0], a[1, 1], a[2, 2], a[3, 3], a[4, 0], a[5, 1], a[6, 2] = 0.0, -0.0, np.inf, -np.inf, np.nan, 1e-320, 1.7976931348623157e308
+    ours, ref = str(tmp_path / "ours.txt"), str(tmp_path / "ref.txt")
+    _lib.write_rows_text(ours, a, header="# one\n# two\n")
+    with open(ref, "w") as f:
+        f.write("# one\n# two\n")
+        np.savetxt(f, a)
+    assert open(ours, "rb").read() == open(ref, "rb").read()
+    _lib.write_rows_text(ours, a[::3, 1:3], append=True, threads=3)
+    with open(ref, "a") as f:
+        np.savetxt(f, a[::3, 1:3])
+    assert open(ours, "rb").read() == open(ref, "rb").read()
+    _lib.write_rows_text(ours, [3.25])
+    np.savetxt(ref, [3.25])
+    assert open(ours, "rb").read() == open(ref, "rb").read()
+    _lib.write_rows_text(ours, np.zeros((0, 4)))
+    assert open(ours, "rb").read() == b""
+    with pytest.raises(_lib.PhfError):
+        _lib.write_rows_text(str(tmp_path / "no_such_dir" / "x.txt"), a[:2])
