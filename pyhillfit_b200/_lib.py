@@ -134,9 +134,10 @@ def write_rows_text(path, array, header=None, append=False, threads=0):
         a = a.reshape(-1, 1)                      # numpy writes a 1-D array one value per line
     if a.ndim != 2:
         raise ValueError("expected a 1-D or 2-D array")
-    if a.strides[1] != 8 or a.strides[0] % 8 != 0 or a.strides[0] < 8 * a.shape[1]:
+    if a.shape[0] == 0 or a.strides[1] != 8 or a.strides[0] % 8 != 0 or a.strides[0] < 8 * a.shape[1]:
         a = np.ascontiguousarray(a)
+    stride = a.strides[0] // 8 if a.shape[0] > 0 else a.shape[1]
     hdr = None if header is None else header.encode("utf-8")
     check(load().phf_write_rows_text_host(os.fsencode(path), hdr, a.ctypes.data, a.shape[0], a.shape[1],
-                                          a.strides[0] // 8, int(bool(append)), int(threads)),
+                                          stride, int(bool(append)), int(threads)),
           "phf_write_rows_text_host")
