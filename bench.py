@@ -247,6 +247,7 @@ def main():
     ap.add_argument("--thinning", type=int, default=5)
     ap.add_argument("--ref-iters-per-step", type=int, default=4000)
     ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-segments", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--block-threads", type=int, default=0)
@@ -543,8 +544,8 @@ def run_e2e(args, torch, dev, pack, wl, samplers, rank, world, dist):
                             block_threads=samplers[model].block_threads)
         rc = L.phf_am_single_run_host(C.byref(cfg), j["n"], j["state"].data_ptr(), j["ids"].ctypes.data,
                                       j["temps"].ctypes.data, pack.n_datasets, pack.datasets.ctypes.data,
-                                      len(pack.groups), pack.groups.ctypes.data, j["samples"].data_ptr(), 8,
-                                      dev.index)
+                                      len(pack.groups), pack.groups.ctypes.data, j["samples"].data_ptr(),
+                                      args.e2e_segments, dev.index)
         _lib.check(rc, "phf_am_single_run_host")
         j["t0"] += K
 
@@ -571,7 +572,7 @@ def run_e2e(args, torch, dev, pack, wl, samplers, rank, world, dist):
         dt = float(tt.item())
     total = float(sum(j["n"] for j in jobs.values())) * K * args.e2e_steps * world
     return {"value": total / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "steps": args.e2e_steps, "api": "phf_am_single_run_host (pinned host buffers, 8 overlapped segments/call)",
+            "steps": args.e2e_steps, "api": "phf_am_single_run_host (pinned host buffers, %d overlapped segments/call)" % args.e2e_segments,
             "timing": "host wall clock around synchronous calls (each call ends with a stream synchronise)"}
 
 
