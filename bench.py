@@ -300,6 +300,7 @@ def main():
     bytes_iter = sum((wl[m]["d"] + 1) * 8.0 / thin * len(wl[m]["ids"]) for m in (1, 2)) / n_chains
 
     main_stream = torch.cuda.current_stream(dev)
+    stream_events = None
 
     def step():
         if args.serial_models:
@@ -312,7 +313,13 @@ def main():
             st = streams[model]
             st.wait_event(ev)
             with torch.cuda.stream(st):
+                if stream_events is not None:   # per-launch duration on the launching stream
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(st)
                 samplers[model].run(K, samples=buffers[model])
+                if stream_events is not None:
+                    b.record(st)
+                    stream_events[model].append((a, b))
         for model in (1, 2):
             main_stream.wait_stream(streams[model])
 
@@ -333,6 +340,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_begin = time.time()
+    stream_events = {1: [], 2: []}
     e0.record(main_stream)
     for _ in range(args.steps):
         step()
@@ -340,6 +348,9 @@ def main():
     barrier()
     t_end = time.time()
     ms = e0.elapsed_time(e1)
+    launch_ms_timed = {m: float(np.mean([a.elapsed_time(b) for a, b in stream_events[m]])) if stream_events[m] else None
+                       for m in (1, 2)}
+    stream_events = None
     launches = _lib.launch_count() - launches0
     clk = clocks.stop(t_begin, t_end) if rank == 0 else None
     if world > 1:
@@ -387,9 +398,14 @@ def main():
         return 0
 
     peak_tf, _ = _lib.fp64_peak_tflops(5)
-    # dominant kernel = the model-2 sampler launch (am_single_kernel<2>)
+    # The hot path is ONE kernel template, am_single_kernel<MODEL, LANES>, launched once per model per step; the two
+    # launches run on two streams and share the SMs for the whole step (each lasts ~ the step).  Its roofline entry
+    # is therefore taken over the timed region itself: algorithmic flops of both launches / (their common duration
+    # = mean step time).  The model-2 launch timed alone (under-occupied at 13 440 chains) is reported beside it.
     n2 = samplers[2].n
-    ach_tf = n2 * K * wl[2]["flops"] / (kern_ms[2] * 1e-3) / 1e12
+    step_flops = sum(samplers[m].n * K * wl[m]["flops"] for m in (1, 2))
+    ach_tf = step_flops / (ms / args.steps * 1e-3) / 1e12
+    alone_tf = n2 * K * wl[2]["flops"] / (kern_ms[2] * 1e-3) / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -399,17 +415,22 @@ def main():
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["am_single_kernel<2>"]
-        traffic = tr["dram_bytes_per_chain_iteration"] * n2 * K
+        traffic = tr["dram_bytes_per_chain_iteration"] * n_chains * K * (bytes_iter / 6.4)
     except Exception:
         pass
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                "traffic": traffic, "kernel": "am_single_kernel<2>", "launch_ms": kern_ms[2],
-                "flops_per_chain_iteration": wl[2]["flops"],
+                "traffic": traffic,
+                "kernel": "am_single_kernel<model 1 | model 2, %d lanes per chain> (two co-resident launches per step)"
+                          % samplers[2].lanes,
+                "launch_ms": ms / args.steps, "launch_ms_on_stream": launch_ms_timed,
+                "flops_per_chain_iteration": flops_iter,
                 "peak_source": "phf_fp64_peak_probe (live DFMA microbenchmark; MEASURED_PEAKS.json has no FP64 entry)",
-                "algorithmic_bytes": n2 * K * (4 * 8.0 / thin),
-                "hbm": {"achieved_gbs": n2 * K * (4 * 8.0 / thin) / (kern_ms[2] * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                "algorithmic_bytes": n_chains * K * bytes_iter,
+                "model2_launch_alone": {"launch_ms": kern_ms[2], "achieved": alone_tf, "frac": alone_tf / peak_tf,
+                                        "flops_per_chain_iteration": wl[2]["flops"]},
+                "hbm": {"achieved_gbs": n_chains * K * bytes_iter / (ms / args.steps * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
-                        "algorithmic_bytes_per_chain_iteration": 4 * 8.0 / thin}}
+                        "algorithmic_bytes_per_chain_iteration": bytes_iter}}
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         r, cores, wall = cpu_reference_rate(6000, warm=300)
@@ -470,16 +491,26 @@ def other_configs(torch, dev, pack):
     temps = (np.arange(64.) / 63) ** 3
     ids, tt = ti.build_chain_list(pack.n_datasets, temps, 1)
     K = 5000
-    tot_t, tot_n = 0.0, 0
+    ss, bufs, strs = {}, {}, {}
     for model in (1, 2):
         d = 2 if model == 1 else 3
-        s = SingleLevelSampler(model, pack, ids, tt, np.ones((len(ids), d)), variant="temp", seed=1, thinning=5,
-                               burn_rows=K // 20, device=dev)
-        buf = torch.empty((s.n, K // 5, d + 1), dtype=torch.float64, device=dev)
-        tot_t += _timed(torch, lambda: s.run(K, samples=buf))
-        tot_n += s.n
-    out["config4_ti_64_temperatures"] = {"chains": tot_n, "iters": K, "value": tot_n * K / tot_t, "unit": UNIT,
-                                         "note": "models 1 and 2 launched back to back"}
+        ss[model] = SingleLevelSampler(model, pack, ids, tt, np.ones((len(ids), d)), variant="temp", seed=1, thinning=5,
+                                       burn_rows=K // 20, device=dev, co_resident_chains=len(ids))
+        bufs[model] = torch.empty((len(ids), K // 5, d + 1), dtype=torch.float64, device=dev)
+        strs[model] = torch.cuda.Stream(device=dev)
+
+    def both():
+        cur = torch.cuda.current_stream(dev)
+        for model in (1, 2):
+            strs[model].wait_stream(cur)
+            with torch.cuda.stream(strs[model]):
+                ss[model].run(K, samples=bufs[model])
+        for model in (1, 2):
+            cur.wait_stream(strs[model])
+    t4 = _timed(torch, both)
+    out["config4_ti_64_temperatures"] = {"chains": 2 * len(ids), "iters": K, "value": 2 * len(ids) * K / t4, "unit": UNIT,
+                                         "note": "models 1 and 2 on two streams, samples written"}
+    del ss, bufs
     # config 5 share: 125 000 synthetic datasets x 4 chains = 500 000 chains, model 2, one thread per chain
     concs, Y, _ = synthetic.generate(125000)
     sp = SinglePack.from_uniform(concs, Y)

@@ -49,31 +49,40 @@ def run_ti(datasets, models=(1, 2), temps=None, replicates=1, iterations=500000,
     num_saved = iterations // thinning + 1
     burn = num_saved // burn_in_fraction
     out = {"temps": temps, "means": {}, "log_py": {}, "acceptance": {}}
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ids, tt = build_chain_list(n_pairs, temps, R)
+    n_groups = pack.datasets["n_groups"][ids].astype(np.float64)
+    bounds = phf_dist.shard_bounds(n_groups, ws)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    # the models are independent: their launches go to separate streams and share the SMs
+    samplers, streams = {}, {}
+    if hi > lo:
+        for model in models:
+            d = 2 if model == 1 else 3
+            samplers[model] = SingleLevelSampler(model, pack, ids[lo:hi], tt[lo:hi], np.ones((hi - lo, d)),
+                                                 variant="temp", seed=seed, chain_id_base=(model - 1) * (1 << 40) + lo,
+                                                 thinning=thinning, burn_rows=burn, device=dev, lanes=lanes,
+                                                 co_resident_chains=(hi - lo) * (len(models) - 1))
+            streams[model] = torch.cuda.Stream(device=dev)
+        torch.cuda.synchronize(dev)
+        done = 0
+        while done < iterations:
+            k = min(segment, iterations - done)
+            for model in models:
+                with torch.cuda.stream(streams[model]):
+                    samplers[model].run(k, keep=False)
+            done += k
+            if progress:
+                progress(done, iterations)
+        torch.cuda.synchronize(dev)
     for model in models:
         d = 2 if model == 1 else 3
-        ids, tt = build_chain_list(n_pairs, temps, R)
-        n_groups = pack.datasets["n_groups"][ids].astype(np.float64)
-        bounds = phf_dist.shard_bounds(n_groups, ws)
-        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-        base = (model - 1) * (1 << 40)
+        nt = d * (d + 1) // 2
         if hi > lo:
-            s = SingleLevelSampler(model, pack, ids[lo:hi], tt[lo:hi], np.ones((hi - lo, d)), variant="temp",
-                                   seed=seed, chain_id_base=base + lo, thinning=thinning, burn_rows=burn,
-                                   device=device, lanes=lanes)
-            done = 0
-            while done < iterations:
-                k = min(segment, iterations - done)
-                s.run(k, keep=False)
-                done += k
-                if progress:
-                    progress(model, done, iterations)
-            st = s.state
-            nt = d * (d + 1) // 2
-            counted = num_saved - burn
-            local_means = st[:, 2 * d + 3 + nt] / counted
+            st = samplers[model].state
+            local_means = st[:, 2 * d + 3 + nt] / (num_saved - burn)
             local_acc = st[:, 2 * d + 4 + nt] / iterations
         else:
-            dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
             local_means = torch.zeros(0, dtype=torch.float64, device=dev)
             local_acc = torch.zeros(0, dtype=torch.float64, device=dev)
         means = phf_dist.all_gather_varlen(local_means, bounds).cpu().numpy().reshape(n_pairs, T, R)
