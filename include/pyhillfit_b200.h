@@ -146,14 +146,19 @@ typedef struct phf_hier_priors {
     double pic50_lower;                   /* -2: PyHillFit.py:215 */
 } phf_hier_priors;
 
-#define PHF_HIER_MAX_EXPTS 13 /* dim <= 31: one warp lane per parameter row */
+#define PHF_HIER_MAX_EXPTS 13      /* dim <= 31: the fast kernels, one warp lane per parameter row */
+#define PHF_HIER_BIG_MAX_EXPTS 128 /* dim <= 261: one warp per chain, state in shared / global memory (the
+                                      50-experiment groups of data/synthetic_data.csv have dim 105) */
 
-/* theta rows have stride `theta_stride` doubles (>= dim of the row's dataset). */
+/* theta rows have stride `theta_stride` doubles (>= dim of the row's dataset; a stride above 31 selects the
+ * warp-per-vector kernel, which accepts up to PHF_HIER_BIG_MAX_EXPTS experiments). */
 int phf_hier_log_target_batch(int64_t n, const double *theta, int32_t theta_stride, const int32_t *dataset_id,
                               const phf_hier_dataset *datasets, const phf_hier_point *points,
                               const phf_hier_priors *priors /* HOST pointer */, double *log_target, void *stream);
 
-/* All chains of one call share n_expts (so dim); state rows are PHF_STATE_SIZE(dim) doubles. */
+/* All chains of one call share n_expts (so dim); state rows are PHF_STATE_SIZE(dim) doubles.
+ * n_expts <= PHF_HIER_MAX_EXPTS: lane-per-parameter kernels; up to PHF_HIER_BIG_MAX_EXPTS: warp-per-chain kernel
+ * (takes a stream-ordered temporary of n_chains * dim (dim+1) / 2 doubles for the Cholesky factors). */
 int phf_am_hier_init(int32_t n_expts, int64_t n_chains, const double *theta0 /* [n,dim] */,
                      const double *cov0_tri /* [n, dim(dim+1)/2] */, const int32_t *dataset_id,
                      const phf_hier_dataset *datasets, const phf_hier_point *points,

@@ -349,6 +349,14 @@ static int launch_am_hier(const phf_am_config &cfg, int64_t n, double *state, co
     return check_launch("am_hier_kernel");
 }
 
+// phf_hier_big.cu
+int hier_big_target_launch(int64_t n, const double *theta, int32_t theta_stride, const double *cov0,
+                           const int32_t *dataset_id, const phf_hier_dataset *datasets, const phf_hier_point *points,
+                           const phf_hier_priors &pr, double *out, double *state, cudaStream_t s);
+int am_hier_big_launch(const phf_am_config &cfg, int32_t n_expts, int64_t n, double *state, const int32_t *dataset_id,
+                       const phf_hier_dataset *datasets, const phf_hier_point *points, const phf_hier_priors &pr,
+                       double *samples, cudaStream_t s);
+
 }  // namespace phf
 
 using namespace phf;
@@ -362,6 +370,11 @@ extern "C" int phf_hier_log_target_batch(int64_t n, const double *theta, int32_t
         return set_error(PHF_EINVAL, "phf_hier_log_target_batch: null pointer");
     if (theta_stride < 7) return set_error(PHF_EINVAL, "theta_stride < 7");
     if (n == 0) return PHF_OK;
+    if (theta_stride > 31) {
+        if (theta_stride > 5 + 2 * PHF_HIER_BIG_MAX_EXPTS + 64) return set_error(PHF_ENOTSUP, "theta_stride too large");
+        return hier_big_target_launch(n, theta, theta_stride, nullptr, dataset_id, datasets, points, *priors, log_target,
+                                      nullptr, (cudaStream_t)stream);
+    }
     const int block = 128;
     const unsigned grid = (unsigned)((n * 32 + block - 1) / block);
     hier_log_target_batch_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n, theta, theta_stride, dataset_id,
@@ -375,11 +388,14 @@ extern "C" int phf_am_hier_init(int32_t n_expts, int64_t n_chains, const double 
                                 const phf_hier_point *points, const phf_hier_priors *priors, double *state,
                                 void *stream)
 {
-    if (n_expts < 1 || n_expts > PHF_HIER_MAX_EXPTS) return set_error(PHF_ENOTSUP, "n_expts outside 1..13");
+    if (n_expts < 1 || n_expts > PHF_HIER_BIG_MAX_EXPTS) return set_error(PHF_ENOTSUP, "n_expts outside 1..128");
     if (n_chains < 0 || !priors ||
         (n_chains > 0 && (!theta0 || !cov0_tri || !dataset_id || !datasets || !points || !state)))
         return set_error(PHF_EINVAL, "phf_am_hier_init: null pointer");
     if (n_chains == 0) return PHF_OK;
+    if (n_expts > PHF_HIER_MAX_EXPTS)
+        return hier_big_target_launch(n_chains, theta0, 5 + 2 * n_expts, cov0_tri, dataset_id, datasets, points, *priors,
+                                      nullptr, state, (cudaStream_t)stream);
     const int block = 128;
     const unsigned grid = (unsigned)((n_chains * 32 + block - 1) / block);
     am_hier_init_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(5 + 2 * n_expts, n_chains, theta0, cov0_tri,
@@ -394,7 +410,7 @@ extern "C" int phf_am_hier_run(const phf_am_config *cfg, int32_t n_expts, int64_
                                void *stream)
 {
     if (!cfg || !priors) return set_error(PHF_EINVAL, "phf_am_hier_run: cfg/priors is NULL");
-    if (n_expts < 1 || n_expts > PHF_HIER_MAX_EXPTS) return set_error(PHF_ENOTSUP, "n_expts outside 1..13");
+    if (n_expts < 1 || n_expts > PHF_HIER_BIG_MAX_EXPTS) return set_error(PHF_ENOTSUP, "n_expts outside 1..128");
     if (cfg->thinning == 0) return set_error(PHF_EINVAL, "cfg.thinning must be >= 1");
     if (n_chains < 0 || (n_chains > 0 && (!state || !dataset_id || !datasets || !points)))
         return set_error(PHF_EINVAL, "phf_am_hier_run: null pointer");
@@ -404,6 +420,8 @@ extern "C" int phf_am_hier_run(const phf_am_config *cfg, int32_t n_expts, int64_
         return set_error(PHF_EINVAL, "cfg.rows_capacity is smaller than the rows this call produces");
     if (n_chains == 0 || cfg->n_iters == 0) return PHF_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    if (n_expts > PHF_HIER_MAX_EXPTS)
+        return am_hier_big_launch(*cfg, n_expts, n_chains, state, dataset_id, datasets, points, *priors, samples, s);
 #define PHF_HIER_CASE(NE, G) \
     case NE: return launch_am_hier<G, 5 + 2 * NE>(*cfg, n_chains, state, dataset_id, datasets, points, *priors, samples, s)
     switch (n_expts) {

@@ -44,7 +44,7 @@ def test_bad_arguments_return_codes_without_a_gpu():
     cfg = _lib.AmConfig(model=2, thinning=5, n_iters=10, lanes_per_chain=3)
     assert L.phf_am_single_run(C.byref(cfg), 0, None, None, None, None, None, None, None) == 0
     pr = _lib.HierPriors()
-    assert L.phf_am_hier_run(C.byref(cfg), 14, 1, None, None, None, None, C.byref(pr), None, None) == -3  # PHF_ENOTSUP
+    assert L.phf_am_hier_run(C.byref(cfg), 129, 1, None, None, None, None, C.byref(pr), None, None) == -3  # PHF_ENOTSUP
     assert L.phf_hier_log_target_batch(0, None, 17, None, None, None, C.byref(pr), None, None) == 0
 
 

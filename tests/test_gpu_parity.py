@@ -151,3 +151,41 @@ def test_hier_log_target_matches_oracle_random(table, hier_pack):
         got = hier_log_target_batch(hier_pack, pad, np.full(n, ip, dtype=np.int32), pr).cpu().numpy()
         assert_close(got, want, what="%s/%s" % (drug, channel))
         assert np.isfinite(want).mean() > 0.2
+
+
+def test_hier_many_experiments_target(table):
+    """The warp-per-chain path (dim > 31): the 50-experiment group of data/synthetic_data.csv (dim 105) against the C
+    oracle, and the same kernel on Crumb pairs (theta rows padded beyond 31) against the reference golden values."""
+    from pyhillfit_b200.packing import HierPack
+    from pyhillfit_b200.sampler import hier_log_target_batch, hier_priors
+    pr, shapes, scales, locs = hier_priors()
+    syn = Table("synthetic_data")
+    by_ne = {len(syn.experiments(d, c)): (d, c) for d, c in syn.pairs()}
+    assert 50 in by_ne
+    ex = syn.experiments(*by_ne[50])
+    ne, dim = 50, 105
+    rng = np.random.default_rng(50)
+    n = 600
+    th = np.zeros((n, dim))
+    th[:, 0] = rng.uniform(0.05, 3, n)
+    th[:, 1] = rng.uniform(1.95, 12, n)
+    th[:, 2] = rng.uniform(-4.2, 10, n)
+    th[:, 3] = rng.uniform(0.009, 2, n)
+    th[:, 4:-1:2] = rng.uniform(3, 9, (n, ne))
+    th[:, 5:-1:2] = rng.uniform(0.2, 3, (n, ne))
+    th[:30, 4] = rng.uniform(-2.1, -1.9, 30)           # around the pIC50 support edge
+    th[30:60, 7] = rng.uniform(-0.01, 0.01, 30)        # around the Hill support edge
+    th[:, -1] = np.exp(rng.uniform(np.log(0.05), np.log(40.), n))
+    want = c_oracle.hier_log_target_batch(ex, th, shapes, scales, locs)
+    pack = HierPack([ex])
+    got = hier_log_target_batch(pack, th, np.zeros(n, dtype=np.int32), pr).cpu().numpy()
+    assert_close(got, want, what="synthetic 50 experiments")
+    assert 0.3 < np.isfinite(want).mean() < 1.0
+    # same kernel, small dims: golden values of the unmodified reference
+    g = np.load(os.path.join(GOLD, "hier_target_golden.npz"))
+    cpack = HierPack([table.experiments(d, c) for d, c in table.pairs()])
+    npairs, nt, stride = g["theta"].shape
+    pad = np.ones((npairs * nt, 40))
+    pad[:, :stride] = np.nan_to_num(g["theta"].reshape(-1, stride), nan=1.0)
+    got = hier_log_target_batch(cpack, pad, np.repeat(np.arange(npairs, dtype=np.int32), nt), pr).cpu().numpy()
+    assert_close(got.reshape(npairs, nt), g["log_target"], what="warp-per-vector kernel on Crumb pairs")

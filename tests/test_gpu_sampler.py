@@ -191,3 +191,32 @@ def test_posterior_quantiles_match_reference_chains(table, model):
             g["ladder_m%d_ll1_ess" % model][it])
         gpu_se = ll1[j].std(ddof=1) / np.sqrt(nch)
         assert abs(ll1[j].mean() - ref_m) <= 5 * np.hypot(ref_se, gpu_se) + 1e-9, (it, ll1[j].mean(), ref_m, ref_se)
+
+
+def test_hier_many_experiments_trajectory():
+    """dim 105 (50 experiments, data/synthetic_data.csv): the warp-per-chain sampler follows the C oracle step by
+    step, across a launch boundary."""
+    from pyhillfit_b200.packing import HierPack
+    from pyhillfit_b200.sampler import HierarchicalSampler, hier_priors, variant_defaults
+    pr, shapes, scales, locs = hier_priors()
+    syn = Table("synthetic_data")
+    ex = [syn.experiments(d, c) for d, c in syn.pairs() if len(syn.experiments(d, c)) == 50][0]
+    ne, dim = 50, 105
+    rng = np.random.default_rng(1)
+    nch = 3
+    theta0 = np.concatenate([np.tile([1.0, 4.0, 6.0, 0.3], (nch, 1)),
+                             np.tile([6.0, 1.0], (nch, ne)) + rng.uniform(-0.2, 0.2, (nch, 2 * ne)),
+                             np.full((nch, 1), 8.0)], axis=1)
+    iters, thin, adapt_when, seed, base = 120, 5, 40, 8, 77
+    s = HierarchicalSampler(HierPack([ex]), np.zeros(nch, dtype=np.int32), theta0, pr, adapt_when=adapt_when,
+                            seed=seed, chain_id_base=base, thinning=thin)
+    got = np.concatenate([s.run(70).cpu().numpy(), s.run(50).cpu().numpy()], axis=1)
+    cov0, _, _ = variant_defaults("hier", theta0)
+    f = s.state_fields()
+    for k in range(nch):
+        want0 = c_oracle.hier_log_target_batch(ex, theta0[k][None], shapes, scales, locs)[0]
+        st = c_oracle.make_state(theta0[k], want0, 0.0, cov0[k])
+        want = c_oracle.am_hier(ex, shapes, scales, locs, st, 0, iters, thin, adapt_when, seed, base + k)
+        assert np.allclose(got[k], want, rtol=1e-7, atol=1e-7), "chain %d diverged" % k
+        assert f["n_accepted"][k] == st[-1]
+    assert f["n_accepted"].sum() > 0
