@@ -169,6 +169,18 @@ int phf_am_hier_run(const phf_am_config *cfg, int32_t n_expts, int64_t n_chains,
                     const phf_hier_priors *priors /* HOST */, double *samples /* [n, rows_capacity, dim+1] */,
                     void *stream);
 
+/*
+ * Posterior-predictive distributions of Hill and pIC50 from hierarchical chain rows.  Replaces
+ * construct_posterior_predictive_cdfs (python/construct_hierarchical_cdfs.py:32-58): `rows` holds n_rows post-burn
+ * rows whose first four entries are (alpha, beta, mu, s), `row_stride` doubles apart (a hierarchical chain /
+ * samples buffer can be passed as is); the grids are np.linspace(hill_min, hill_max, n_x) and
+ * np.linspace(pic50_min, pic50_max, n_x) (the reference: 0..4, -2..12, 501 points).
+ *   out [4, n_x]: mean over rows of fisk.cdf, fisk.pdf (c = beta, scale = alpha) on the Hill grid, then of
+ *                 logistic.cdf, logistic.pdf (loc = mu, scale = s) on the pIC50 grid.
+ */
+int phf_hier_predictive_cdfs(int64_t n_rows, const double *rows, int32_t row_stride, int32_t n_x, double hill_min,
+                             double hill_max, double pic50_min, double pic50_max, double *out, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry point (the reference-facing call: numpy arrays in, numpy arrays out).
  * Every pointer is a HOST pointer (pinned memory makes the copies asynchronous).  One call = copy state

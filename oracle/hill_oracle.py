@@ -364,3 +364,24 @@ def adaptive_metropolis(target, theta0, iterations, thinning, variant, rng="nump
         state_out.update(theta=theta_cur, log_target=log_target_cur, mean=mean, cov=cov, loga=loga,
                          acceptance=acceptance)
     return chain, acceptance
+
+
+# ----------------------------------------------------------------------------
+# posterior-predictive CDFs -- python/construct_hierarchical_cdfs.py:32-58
+# ----------------------------------------------------------------------------
+def construct_posterior_predictive_cdfs(alphas, betas, mus, ss):
+    num_x_pts = 501
+    hill_x_range = np.linspace(0., 4., num_x_pts)
+    pic50_x_range = np.linspace(-2., 12., num_x_pts)
+    num_iterations = len(alphas)
+    hill_pdf_sum = np.zeros(num_x_pts)
+    hill_cdf_sum = np.zeros(num_x_pts)
+    pic50_pdf_sum = np.zeros(num_x_pts)
+    pic50_cdf_sum = np.zeros(num_x_pts)
+    for i in range(num_iterations):
+        hill_cdf_sum += st.fisk.cdf(hill_x_range, c=betas[i], scale=alphas[i], loc=0)
+        hill_pdf_sum += st.fisk.pdf(hill_x_range, c=betas[i], scale=alphas[i], loc=0)
+        pic50_cdf_sum += st.logistic.cdf(pic50_x_range, mus[i], ss[i])
+        pic50_pdf_sum += st.logistic.pdf(pic50_x_range, mus[i], ss[i])
+    return (hill_x_range, hill_cdf_sum / num_iterations, pic50_x_range, pic50_cdf_sum / num_iterations,
+            hill_pdf_sum / num_iterations, pic50_pdf_sum / num_iterations)

@@ -30,6 +30,7 @@ def available():
 def _py2to3(src):
     src = re.sub(r'^(\s*)print (.*)$', r'\1print(\2)', src, flags=re.M)
     src = src.replace("raw_input(", "input(").replace("xrange(", "range(")
+    src = re.sub(r'except (\w+)\s*,\s*(\w+):', r'except \1 as \2:', src)   # py2 "except Exception,e:"
     return src
 
 
@@ -93,3 +94,15 @@ def load_do_mcmc(dr, namespace):
     code = _extract_functions(os.path.join(REF_ROOT, "python", "PyHillTemp.py"), ["do_mcmc"], int_div=True)
     exec(code, ns)
     return ns["do_mcmc"], ns
+
+
+def load_construct_cdfs():
+    """python/construct_hierarchical_cdfs.py:32-58 `construct_posterior_predictive_cdfs` (the script itself runs
+    argparse at import, so only the function is extracted)."""
+    import numpy as np
+    import scipy.stats as st
+    ns = {"np": np, "st": st, "xrange": range}
+    code = _extract_functions(os.path.join(REF_ROOT, "python", "construct_hierarchical_cdfs.py"),
+                              ["construct_posterior_predictive_cdfs"])
+    exec(code, ns)
+    return ns["construct_posterior_predictive_cdfs"]

@@ -189,3 +189,29 @@ def test_hier_many_experiments_target(table):
     pad[:, :stride] = np.nan_to_num(g["theta"].reshape(-1, stride), nan=1.0)
     got = hier_log_target_batch(cpack, pad, np.repeat(np.arange(npairs, dtype=np.int32), nt), pr).cpu().numpy()
     assert_close(got.reshape(npairs, nt), g["log_target"], what="warp-per-vector kernel on Crumb pairs")
+
+
+def test_posterior_predictive_cdfs_match_reference():
+    """phf_hier_predictive_cdfs vs the unmodified reference function (tests/golden/cdf_golden.npz: 3000 rows incl. a
+    logistic narrower than the grid step and a very steep log-logistic) and vs the oracle on a strided chain buffer.
+    Tolerance 1e-11 relative (+1e-300): the reference sums 3000 terms sequentially, the kernel in 128-row tiles."""
+    import torch
+    from pyhillfit_b200.construct_hierarchical_cdfs import (construct_posterior_predictive_cdfs,
+                                                            predictive_cdfs_from_rows)
+    g = np.load(os.path.join(GOLD, "cdf_golden.npz"))
+    r = g["rows"]
+    hx, hc, px, pc, hp, pp = construct_posterior_predictive_cdfs(r[:, 0], r[:, 1], r[:, 2], r[:, 3])
+    assert np.array_equal(hx, g["hill_x"]) and np.array_equal(px, g["pic50_x"])
+    for got, key in ((hc, "hill_cdf"), (pc, "pic50_cdf"), (hp, "hill_pdf"), (pp, "pic50_pdf")):
+        want = g[key]
+        assert np.all(np.abs(got - want) <= 1e-11 * np.abs(want) + 1e-300), (key, np.max(np.abs(got - want)))
+    assert hc[0] == 0.0 and abs(pc[-1] - 1) < 0.01
+    # a chain-shaped device buffer (12 columns, first four used), few rows
+    rng = np.random.default_rng(3)
+    chain = rng.uniform(0.5, 3.0, (37, 12))
+    chain[:, 1] += 2.0
+    with np.errstate(all="ignore"):
+        want = ho.construct_posterior_predictive_cdfs(chain[:, 0], chain[:, 1], chain[:, 2], chain[:, 3])
+    got = predictive_cdfs_from_rows(torch.from_numpy(chain).cuda())
+    for k, j in ((0, 1), (1, 4), (2, 3), (3, 5)):
+        assert np.allclose(got[k], want[j], rtol=1e-12, atol=1e-300)

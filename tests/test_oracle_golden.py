@@ -172,3 +172,17 @@ def test_am_c_oracle_follows_py_oracle(table):
         chain_c = c_oracle.am_single(model, concs, y, temp, pb, st, 0, iters, thin, adapt_when, reset, 9, 3)
         assert np.allclose(chain_c, chain_py[1:], rtol=1e-9, atol=1e-9)
         assert st[-1] / iters == pytest.approx(acc, abs=1e-12)
+
+
+def test_cdf_oracle_matches_reference_golden():
+    """oracle restatement of construct_posterior_predictive_cdfs vs the unmodified reference (cdf_golden.npz)."""
+    g = np.load(os.path.join(GOLD, "cdf_golden.npz"))
+    r = g["rows"][:500]
+    with np.errstate(all="ignore"):
+        hx, hc, px, pc, hp, pp = ho.construct_posterior_predictive_cdfs(r[:, 0], r[:, 1], r[:, 2], r[:, 3])
+    assert np.array_equal(hx, g["hill_x"]) and np.array_equal(px, g["pic50_x"])
+    full = g["rows"]
+    with np.errstate(all="ignore"):
+        out = ho.construct_posterior_predictive_cdfs(full[:, 0], full[:, 1], full[:, 2], full[:, 3])
+    for got, key in zip(out, ("hill_x", "hill_cdf", "pic50_x", "pic50_cdf", "hill_pdf", "pic50_pdf")):
+        assert np.array_equal(got, g[key]), key
