@@ -572,7 +572,7 @@ def run_e2e(args, torch, dev, pack, wl, samplers, rank, world, dist):
         cfg = _lib.AmConfig(model=model, reset_mean_at_adapt=0, t0=j["t0"], n_iters=K, thinning=thin,
                             adapt_when=1000 * wl[model]["d"], burn_rows=0xFFFFFFFF, rows_capacity=rows, seed=25,
                             chain_id_base=(rank * 2 + (model - 1)) * (1 << 32), stage_groups=samplers[model].stage_groups,
-                            block_threads=samplers[model].block_threads)
+                            block_threads=samplers[model].block_threads, lanes_per_chain=samplers[model].lanes)
         rc = L.phf_am_single_run_host(C.byref(cfg), j["n"], j["state"].data_ptr(), j["ids"].ctypes.data,
                                       j["temps"].ctypes.data, pack.n_datasets, pack.datasets.ctypes.data,
                                       len(pack.groups), pack.groups.ctypes.data, j["samples"].data_ptr(),
