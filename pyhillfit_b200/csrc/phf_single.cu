@@ -218,7 +218,11 @@ __global__ void __launch_bounds__(128, MINB)
     const bool active = chain < n;
     const int64_t c = active ? chain : n - 1;
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned mask = group_mask<G>();
+    // Every lane of the warp runs the same iteration count and reaches every shuffle / __syncwarp below (chains past
+    // the end are clamped, not retired), so the full-warp mask is valid for every group size -- the shuffle WIDTH keeps
+    // data inside a group.  A run-time partial mask makes the compiler guard each shuffle with a REDUX.OR + LOP3 +
+    // BRA.DIV convergence check (13 % of the stall samples in the 2-lane profile).
+    const unsigned mask = 0xffffffffu;
 
     // ---- stage this CTA's dose groups (chains are sorted by dataset, so the range is contiguous) ----
     const phf_dataset ds = datasets[dataset_id[c]];
@@ -301,11 +305,11 @@ __global__ void __launch_bounds__(128, MINB)
             const int slot = (int)(it & (uint32_t)(G - 1));
             if (slot == 0) {
                 const Draws<D> mine = make_draws<D>(T, cfg.seed, chain_id, t + (uint32_t)gl);
-                __syncwarp(mask);  // the group has finished reading the previous block's slots
+                __syncwarp();  // the group has finished reading the previous block's slots
                 my_slot[0] = mine.log_u;
 #pragma unroll
                 for (int k = 0; k < D; ++k) my_slot[1 + k] = mine.z[k];
-                __syncwarp(mask);
+                __syncwarp();
             }
             const double *src = chain_slots + slot * (D + 1);
             dr.log_u = src[0];
