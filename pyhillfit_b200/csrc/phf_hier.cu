@@ -60,12 +60,20 @@ PHF_DI HierPoint load_point(const phf_hier_point *p)
 // must call it; the result is uniform across the group.
 template <int G>
 PHF_DI double hier_log_target(const double *T, double th_j, int gl, int dim, const LanePrior &lp, const HierPoint &pt0,
-                              const phf_hier_point *__restrict__ pts, int npts, unsigned mask)
+                              const phf_hier_point *__restrict__ pts, int npts, int npts_warp)
 {
+    // All 32 lanes of the warp call this together and run the same number of data rounds (npts_warp = the larger
+    // point count of the warp's chains), so every shuffle can name the full warp at compile time; the shuffle WIDTH
+    // keeps data inside the G-lane group.  (A run-time partial mask costs a convergence check per shuffle.)
+    constexpr unsigned mask = 0xffffffffu;
     // ---- support (PyHillFit.py:176-183) ----
     bool bad = false;
     if (gl < dim) bad = lp.strict ? !(th_j > lp.lower) : !(th_j >= lp.lower);
-    bad = __any_sync(mask, bad) != 0;
+    {
+        const unsigned votes = __ballot_sync(mask, bad);
+        const unsigned mine = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (threadIdx.x & 31u & ~(unsigned)(G - 1)));
+        bad = (votes & mine) != 0u;
+    }
 
     // ---- one vector log for every entry, one for the Gamma hyper-priors ----
     // (log_pos needs a positive argument: entries that may legitimately be <= 0 -- mu, pIC50_e -- never use theirs;
@@ -105,7 +113,7 @@ PHF_DI double hier_log_target(const double *T, double th_j, int gl, int dim, con
     const double inv_s = fm::rcp(sigma);
     const double inv2s2 = 0.5 * inv_s * inv_s;
     const double inv_s_rt2 = inv_s * kSqrtHalf;
-    for (int base = 0; base < npts; base += G) {
+    for (int base = 0; base < npts_warp; base += G) {
         const int pi = base + gl;
         const bool has = pi < npts;
         HierPoint P = pt0;
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(128) hier_log_target_batch_kernel(int64_t n, c
     const LanePrior lp = lane_prior(gl, dim, pr);
     const phf_hier_point *pts = points + ds.point_begin;
     const HierPoint pt0 = load_point(pts + (gl < ds.n_points ? gl : 0));
-    const double lt = hier_log_target<G>(T, th_j, gl, dim, lp, pt0, pts, ds.n_points, 0xffffffffu);
+    const double lt = hier_log_target<G>(T, th_j, gl, dim, lp, pt0, pts, ds.n_points, ds.n_points);
     if (gl == 0) out[i] = lt;
 }
 
@@ -179,7 +187,7 @@ __global__ void __launch_bounds__(128) am_hier_init_kernel(int32_t dim, int64_t 
     const LanePrior lp = lane_prior(gl, dim, pr);
     const phf_hier_point *pts = points + ds.point_begin;
     const HierPoint pt0 = load_point(pts + (gl < ds.n_points ? gl : 0));
-    const double lt = hier_log_target<G>(T, th_j, gl, dim, lp, pt0, pts, ds.n_points, 0xffffffffu);
+    const double lt = hier_log_target<G>(T, th_j, gl, dim, lp, pt0, pts, ds.n_points, ds.n_points);
     double *s = state + i * nf;
     if (gl < dim) {
         s[gl] = th_j;
@@ -198,8 +206,12 @@ __global__ void __launch_bounds__(128) am_hier_init_kernel(int32_t dim, int64_t 
 // ------------------------------------------------------------------------------------------------
 // fused adaptive Metropolis, hierarchical (PyHillFit.py:481-511)
 // ------------------------------------------------------------------------------------------------
+// Register budget: each lane keeps a covariance row and a Cholesky row (2 DIM doubles).  128 registers (4 CTAs of
+// 128 threads per SM) hold that up to DIM 15 -- every Crumb pair but three; beyond, fewer resident CTAs.
+constexpr int hier_min_ctas(int dim) { return dim <= 15 ? 4 : (dim <= 23 ? 3 : 2); }
+
 template <int G, int DIM>
-__global__ void __launch_bounds__(128) am_hier_kernel(phf_am_config cfg, int64_t n, double *__restrict__ state,
+__global__ void __launch_bounds__(128, hier_min_ctas(DIM)) am_hier_kernel(phf_am_config cfg, int64_t n, double *__restrict__ state,
                                                       const int32_t *__restrict__ dataset_id,
                                                       const phf_hier_dataset *__restrict__ datasets,
                                                       const phf_hier_point *__restrict__ points, phf_hier_priors pr,
@@ -213,12 +225,13 @@ __global__ void __launch_bounds__(128) am_hier_kernel(phf_am_config cfg, int64_t
     const int64_t chain = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const bool active = chain < n;
     const int64_t c = active ? chain : n - 1;
-    const unsigned mask = group_mask<G>();
+    constexpr unsigned mask = 0xffffffffu;  // see hier_log_target: every lane of the warp reaches every shuffle
 
     const phf_hier_dataset ds = datasets[dataset_id[c]];
     const phf_hier_point *pts = points + ds.point_begin;
     const int npts = ds.n_points;
     const HierPoint pt0 = load_point(pts + (gl < npts ? gl : 0));
+    const int npts_warp = G == 32 ? npts : max(npts, __shfl_xor_sync(0xffffffffu, npts, 16));
     const LanePrior lp = lane_prior(gl, DIM, pr);
     const uint64_t chain_id = cfg.chain_id_base + (uint64_t)c;
 
@@ -289,7 +302,7 @@ __global__ void __launch_bounds__(128) am_hier_kernel(phf_am_config cfg, int64_t
         }
 
         // ---- target, accept (PyHillFit.py:486-493) ----
-        const double lt_star = hier_log_target<G>(T, star_j, gl, DIM, lp, pt0, pts, npts, mask);
+        const double lt_star = hier_log_target<G>(T, star_j, gl, DIM, lp, pt0, pts, npts, npts_warp);
         const bool accepted = fm::log_pos(T, u) < lt_star - lt;
         if (accepted) {
             th_j = star_j;
