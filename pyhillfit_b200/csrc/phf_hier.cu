@@ -247,10 +247,15 @@ __global__ void __launch_bounds__(128, hier_min_ctas(DIM)) am_hier_kernel(phf_am
     double loga = sp[2 * DIM + 2 + NT];
     double n_acc = sp[2 * DIM + 2 + NT + 2];
 
-    // ---- this lane's slice of the Philox stream: normal pair q = j/2 (contract: oracle/hill_oracle.py) ----
-    const uint32_t q = (uint32_t)gl >> 1;
+    // ---- draws (contract: oracle/hill_oracle.py): normal pair q feeds parameters 2q, 2q+1; they depend on t only, so
+    //      the G lanes prepare TWO iterations at a time: lane L < G/2 makes pair L of iteration t, lane L >= G/2 pair
+    //      L - G/2 of iteration t+1 (DIM < G, so at most G/2 pairs).  Lanes with pair 0 also hold log(u). ----
+    constexpr int H = G / 2;
+    const uint32_t q = (uint32_t)gl % (uint32_t)H;
+    const uint32_t ahead = (uint32_t)gl / (uint32_t)H;  // 0: this iteration, 1: the next one
     const uint32_t call = q == 0u ? 0u : (q + 1u) >> 1;
     const bool hi_words = (q == 0u) || ((q & 1u) == 0u);  // words 2,3
+    double zz0 = 0.0, zz1 = 0.0, lu = 0.0;
 
     uint32_t t = cfg.t0;
     uint32_t until_save = cfg.thinning - (t % cfg.thinning);
@@ -270,13 +275,18 @@ __global__ void __launch_bounds__(128, hier_min_ctas(DIM)) am_hier_kernel(phf_am
         const double gam = __shfl_sync(0xffffffffu, gam_lane, it & 31u);
 
         // ---- draws ----
-        double z_j, u;
+        const uint32_t par = it & 1u;
+        if (par == 0u) {
+            const Philox4 r = philox_call(cfg.seed, chain_id, t + ahead, call);
+            box_muller(T, hi_words ? r.w[2] : r.w[0], hi_words ? r.w[3] : r.w[1], zz0, zz1);
+            lu = fm::log_pos(T, uniform53(r.w[0], r.w[1]));  // meaningful on the lanes that made call 0
+        }
+        double z_j, log_u;
         {
-            const Philox4 r = philox_call(cfg.seed, chain_id, t, call);
-            double z0, z1;
-            box_muller(T, hi_words ? r.w[2] : r.w[0], hi_words ? r.w[3] : r.w[1], z0, z1);
-            z_j = (gl & 1) ? z1 : z0;
-            u = __shfl_sync(mask, uniform53(r.w[0], r.w[1]), 0, G);  // lane 0 made call 0
+            const int src = (gl >> 1) + (int)par * H;
+            const double a = __shfl_sync(mask, zz0, src, G), b = __shfl_sync(mask, zz1, src, G);
+            z_j = (gl & 1) ? b : a;
+            log_u = __shfl_sync(mask, lu, (int)par * H, G);
         }
 
         // ---- Cholesky factor of the covariance, left-looking, row j on lane j ----
@@ -303,7 +313,7 @@ __global__ void __launch_bounds__(128, hier_min_ctas(DIM)) am_hier_kernel(phf_am
 
         // ---- target, accept (PyHillFit.py:486-493) ----
         const double lt_star = hier_log_target<G>(T, star_j, gl, DIM, lp, pt0, pts, npts, npts_warp);
-        const bool accepted = fm::log_pos(T, u) < lt_star - lt;
+        const bool accepted = log_u < lt_star - lt;
         if (accepted) {
             th_j = star_j;
             lt = lt_star;
