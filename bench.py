@@ -32,6 +32,17 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# stdout carries exactly ONE line, the JSON result: everything else that writes to file descriptor 1 (NCCL prints its
+# version there from C) is sent to stderr for the life of the process.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+sys.stdout = os.fdopen(os.dup(2), "w", buffering=1)
+
+
+def emit(line):
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
+
 METRIC = "chain-iterations/sec (all chains, device-timed)"
 UNIT = "chain-iterations/s"
 WORKLOAD = "Crumb: 210 drug-channel pairs x single-level models {1,2} x %d chains, PyHillFit AM, thinning %d"
@@ -229,7 +240,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -459,7 +470,7 @@ def main():
             "hbm_bytes_per_chain_iteration": bytes_iter, "flops_per_chain_iteration": flops_iter,
             "kernel_ms": {"am_single_kernel<1>": kern_ms[1], "am_single_kernel<2>": kern_ms[2]},
             "other_configs": other}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
