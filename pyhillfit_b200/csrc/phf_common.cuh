@@ -13,13 +13,15 @@ int check_launch(const char *kernel_name);  // cudaGetLastError() -> PHF_OK / PH
 void count_launch();
 int sm_count();
 
-// One chain per thread: prefer 32-thread CTAs until every SM holds >= 16 of them, so that small chain
-// counts spread over all 148 SMs; larger CTAs only once the grid is many waves deep.
-inline int default_block_threads(int64_t n_chains)
+// CTA size for the sampler kernels (`n_threads` = chains x lanes).  Tiny launches use 32-thread CTAs so that every
+// warp gets an SM to itself; up to ~16 warps per SM 64-thread CTAs (measured 4 % faster than 32 or 128 when the
+// model-1 and model-2 launches of config 2 share the SMs: two warps of a CTA land on two sub-partitions and the
+// grid still spreads evenly); beyond that 128.
+inline int default_block_threads(int64_t n_threads)
 {
     const int64_t sms = sm_count();
-    if (n_chains <= sms * 16 * 32) return 32;
-    if (n_chains <= sms * 16 * 64) return 64;
+    if (n_threads <= sms * 32) return 32;
+    if (n_threads <= sms * 16 * 64) return 64;
     return 128;
 }
 

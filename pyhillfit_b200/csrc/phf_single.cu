@@ -404,11 +404,11 @@ extern "C" int phf_am_single_init(int model, int64_t n_chains, const double *the
 
 extern "C" int phf_am_single_lanes(int64_t n_chains)
 {
-    // Lanes are added while every lane of every chain can be resident at once at the kernels' full register budget
-    // (128 registers -> 512 threads per SM): measured on B200, a launch that does not fit in one wave, or that fits
+    // Lanes are added while every lane of every chain can be resident at once at the kernels' register budget
+    // (168 registers -> 384 threads per SM): measured on B200, a launch that does not fit in one wave, or that fits
     // only with a tighter register cap (spills), is slower than the same launch with fewer lanes.  `n_chains`
     // should count the chains of ALL launches that run concurrently (e.g. models 1 and 2 on two streams).
-    const int64_t resident = (int64_t)sm_count() * 512;
+    const int64_t resident = (int64_t)sm_count() * 384;
     if (n_chains * 4 <= resident) return 4;
     if (n_chains * 2 <= resident) return 2;
     return 1;
@@ -443,32 +443,32 @@ extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, dou
                         (lanes > 1 ? (size_t)block * ((cfg->model == 1 ? 2 : 3) + 1) * sizeof(double) : 0);
     if (smem > 200 * 1024) return set_error(PHF_EINVAL, "cfg.stage_groups needs more than 200 KB of shared memory");
     cudaStream_t s = (cudaStream_t)stream;
-    const int minb = cfg->reserved > 0 ? cfg->reserved : 4;
+    const int minb = cfg->reserved > 0 ? cfg->reserved : 3;  // 168 registers: no spills; measured best at every size
 #define PHF_AM_CASE(M, G, MINB)                                                                                  \
     if (cfg->model == M && lanes == G && minb == MINB)                                                                       \
         return launch_am_single<M, G, MINB>(*cfg, n_chains, block, smem, state, dataset_id, temperature, datasets, \
                                             groups, samples, s)
+    PHF_AM_CASE(1, 1, 3);
+    PHF_AM_CASE(1, 2, 3);
+    PHF_AM_CASE(1, 4, 3);
+    PHF_AM_CASE(2, 1, 3);
+    PHF_AM_CASE(2, 2, 3);
+    PHF_AM_CASE(2, 4, 3);
+    // other register budgets (cfg.reserved = min CTAs of 128 threads per SM: 2 -> 255 registers, 4 -> 128, 6 -> 80;
+    // developer knob, the sweeps behind the default are in profiles/)
+    PHF_AM_CASE(1, 1, 2);
+    PHF_AM_CASE(1, 2, 2);
+    PHF_AM_CASE(1, 4, 2);
+    PHF_AM_CASE(2, 1, 2);
+    PHF_AM_CASE(2, 2, 2);
+    PHF_AM_CASE(2, 4, 2);
     PHF_AM_CASE(1, 1, 4);
-    PHF_AM_CASE(1, 2, 6);
-    PHF_AM_CASE(1, 4, 6);
-    PHF_AM_CASE(2, 1, 4);
-    PHF_AM_CASE(2, 2, 6);
-    PHF_AM_CASE(2, 4, 6);
-    // other occupancy variants (cfg.reserved = min CTAs of 128 threads per SM; developer knob)
-    PHF_AM_CASE(1, 1, 5);
-    PHF_AM_CASE(1, 1, 6);
     PHF_AM_CASE(1, 2, 4);
-    PHF_AM_CASE(1, 2, 5);
     PHF_AM_CASE(1, 4, 4);
-    PHF_AM_CASE(1, 4, 5);
-    PHF_AM_CASE(1, 4, 8);
-    PHF_AM_CASE(2, 1, 5);
-    PHF_AM_CASE(2, 1, 6);
+    PHF_AM_CASE(2, 1, 4);
     PHF_AM_CASE(2, 2, 4);
-    PHF_AM_CASE(2, 2, 5);
     PHF_AM_CASE(2, 4, 4);
-    PHF_AM_CASE(2, 4, 5);
-    PHF_AM_CASE(2, 4, 8);
+    PHF_AM_CASE(2, 4, 6);
 #undef PHF_AM_CASE
     return set_error(PHF_EINVAL, "no kernel variant for this (model, lanes, occupancy hint)");
 }

@@ -146,11 +146,12 @@ class SingleLevelSampler(_Base):
                 nt = self.d * (self.d + 1) // 2
                 self.state[:, 2 * self.d + 3 + nt] = self.state[:, self.d + 1]
 
-    def _default_block(self, n):
+    def _default_block(self, n_threads):
+        """mirror of default_block_threads (csrc/phf_common.cuh): needed here to size the shared-memory staging"""
         sms = self.torch.cuda.get_device_properties(self.device).multi_processor_count
-        if n <= sms * 16 * 32:
+        if n_threads <= sms * 32:
             return 32
-        if n <= sms * 16 * 64:
+        if n_threads <= sms * 16 * 64:
             return 64
         return 128
 
