@@ -206,9 +206,9 @@ __global__ void __launch_bounds__(128) am_hier_init_kernel(int32_t dim, int64_t 
 // ------------------------------------------------------------------------------------------------
 // fused adaptive Metropolis, hierarchical (PyHillFit.py:481-511)
 // ------------------------------------------------------------------------------------------------
-// Register budget: each lane keeps a covariance row and a Cholesky row (2 DIM doubles).  128 registers (4 CTAs of
-// 128 threads per SM) hold that up to DIM 15 -- every Crumb pair but three; beyond, fewer resident CTAs.
-constexpr int hier_min_ctas(int dim) { return dim <= 15 ? 4 : (dim <= 23 ? 3 : 2); }
+// Register budget: each lane keeps a covariance row and a Cholesky row (2 DIM doubles).  Measured (256 chains per
+// pair): dim 11 is fastest at 128 registers / 4 CTAs per SM, dim 13 and 15 at 168 / 3 (128 spills).
+constexpr int hier_min_ctas(int dim) { return dim <= 11 ? 4 : (dim <= 23 ? 3 : 2); }
 
 template <int G, int DIM>
 __global__ void __launch_bounds__(128, hier_min_ctas(DIM)) am_hier_kernel(phf_am_config cfg, int64_t n, double *__restrict__ state,
