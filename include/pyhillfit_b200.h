@@ -104,7 +104,9 @@ typedef struct phf_am_config {
     int32_t lanes_per_chain;     /* single-level only: 1, 2 or 4 lanes cooperate on one chain; 0: chosen from
                                     n_chains (phf_am_single_lanes).  Results of different lane counts agree to
                                     rounding (the reduction order differs), not bit for bit. */
-    int32_t reserved;
+    int32_t min_ctas_hint;       /* single-level only, 0: library default (3).  Register budget of the kernel variant,
+                                    as the minimum number of 128-thread CTAs per SM it is compiled for: 2 -> 255
+                                    registers, 3 -> 168, 4 -> 128, 6 -> 80.  A tuning knob; results do not depend on it. */
 } phf_am_config;
 
 /* Evaluate the target at theta0 and fill `state` (mean = theta0, cov = cov0, loga = 0, counters = 0). */

@@ -257,7 +257,7 @@ PHF_FM double erfcx_nonneg(const double *T, double t)
 PHF_FM double log_ndtr_nonpos(const double *T, double z)
 {
     const double t = fabs(z) * T[PHF_FM_KMISC + 2];
-    return log_pos(T, 0.5 * erfcx_nonneg(T, t)) - t * t;
+    return fma(-t, t, log_pos(T, 0.5 * erfcx_nonneg(T, t)));
 }
 
 // ---- sin and cos of 2 pi b / 2^32 ---------------------------------------------------------------

@@ -142,6 +142,6 @@ PHF_DI double hill_ratio_pow(const double *T, double lnc_hi, double lnc_lo, doub
 }
 
 // predicted response 100 (1 - 1/(1 + x)) -- python/doseresponse.py:85
-PHF_DI double hill_response(double x) { return 100.0 * (1.0 - fm::rcp(1.0 + x)); }
+PHF_DI double hill_response(double x) { return fma(-100.0, fm::rcp(1.0 + x), 100.0); }
 
 }  // namespace phf

@@ -443,7 +443,7 @@ extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, dou
                         (lanes > 1 ? (size_t)block * ((cfg->model == 1 ? 2 : 3) + 1) * sizeof(double) : 0);
     if (smem > 200 * 1024) return set_error(PHF_EINVAL, "cfg.stage_groups needs more than 200 KB of shared memory");
     cudaStream_t s = (cudaStream_t)stream;
-    const int minb = cfg->reserved > 0 ? cfg->reserved : 3;  // 168 registers: no spills; measured best at every size
+    const int minb = cfg->min_ctas_hint > 0 ? cfg->min_ctas_hint : 3;  // 168 registers: no spills; measured best at every size
 #define PHF_AM_CASE(M, G, MINB)                                                                                  \
     if (cfg->model == M && lanes == G && minb == MINB)                                                                       \
         return launch_am_single<M, G, MINB>(*cfg, n_chains, block, smem, state, dataset_id, temperature, datasets, \
@@ -454,7 +454,7 @@ extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, dou
     PHF_AM_CASE(2, 1, 3);
     PHF_AM_CASE(2, 2, 3);
     PHF_AM_CASE(2, 4, 3);
-    // other register budgets (cfg.reserved = min CTAs of 128 threads per SM: 2 -> 255 registers, 4 -> 128, 6 -> 80;
+    // other register budgets (cfg.min_ctas_hint = min CTAs of 128 threads per SM: 2 -> 255 registers, 4 -> 128, 6 -> 80;
     // developer knob, the sweeps behind the default are in profiles/)
     PHF_AM_CASE(1, 1, 2);
     PHF_AM_CASE(1, 2, 2);

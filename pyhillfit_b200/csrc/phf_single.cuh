@@ -91,7 +91,7 @@ PHF_DI void single_log_target_lanes(const double *T, const double *th, const phf
         log_sm = fm::log_pos(T, sm);
     }
     // log_gamma_prior (doseresponse.py:308) + log_pic50_exponential (:156)
-    const double prior = kSigmaShapeM1 * log_sm - sm * (1.0 / kSigmaScale) - kPic50ExpRate * pic50;
+    const double prior = fma(-kPic50ExpRate, pic50, fma(kSigmaShapeM1, log_sm, -sm * (1.0 / kSigmaScale)));
     bool in_support = sigma_ok && (pic50 >= kPic50ExpLower);
     if (MODEL == 2) in_support = in_support && (hill >= kHillLower) && (hill <= kHillUpper);
 
@@ -146,12 +146,11 @@ PHF_DI void single_log_target_lanes(const double *T, const double *th, const phf
         e2 = group_sum<G>(e2, mask);
         cens = group_sum<G>(cens, mask);
     }
-    const double temp_1 = n_other_total * log_s;
-    const double temp_2 = e2 * (0.5 * inv_s * inv_s);
-    const double raw = cens - pi_bit - temp_1 - temp_2;
+    // cens - pi_bit - n_other ln(sigma) - e2 / (2 sigma^2)   (doseresponse.py:220-222, 246-248)
+    const double raw = fma(-e2, 0.5 * inv_s * inv_s, fma(-n_other_total, log_s, cens - pi_bit));
     loglik_t1 = sigma_ok ? raw : -CUDART_INF;
-    const double lik = temperature == 0.0 ? 0.0 : temperature * raw;  // doseresponse.py:204-205,230-231
-    log_target = in_support ? lik + prior : -CUDART_INF;
+    const double post = temperature == 0.0 ? prior : fma(temperature, raw, prior);  // doseresponse.py:204-205,230-231
+    log_target = in_support ? post : -CUDART_INF;
 }
 
 // single-thread form used by the batch / init kernels (threads may have exited: no warp votes)

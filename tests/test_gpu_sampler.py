@@ -220,3 +220,51 @@ def test_hier_many_experiments_trajectory():
         assert np.allclose(got[k], want, rtol=1e-7, atol=1e-7), "chain %d diverged" % k
         assert f["n_accepted"][k] == st[-1]
     assert f["n_accepted"].sum() > 0
+
+
+@pytest.mark.parametrize("lanes,block,hint", [(1, 32, 2), (1, 128, 4), (2, 64, 0), (2, 128, 4), (4, 32, 0), (4, 96, 6)])
+def test_launch_shapes_do_not_change_results(table, lanes, block, hint):
+    """CTA size, register-budget variant and shared-memory staging are tuning knobs: for a fixed lane count every
+    combination gives the same bits (ragged chain count: the last warp / CTA is partly idle; one dataset with five
+    doses exercises the general-loop path, one with two the predicated-off lanes)."""
+    from pyhillfit_b200.packing import SinglePack
+    from pyhillfit_b200.sampler import SingleLevelSampler
+    pairs = table.pairs()
+    five = [p for p in pairs if len(np.unique(table.concat(*p)[0])) == 5][0]
+    two = [p for p in pairs if len(np.unique(table.concat(*p)[0])) == 2][0]
+    use = [pairs[0], five, two, pairs[7], pairs[33]]
+    pack = SinglePack([table.concat(*p) for p in use])
+    ids = np.repeat(np.arange(len(use), dtype=np.int32), 11)[:-2]          # 53 chains
+    theta0 = np.tile([5.5, 1.0, 6.0], (len(ids), 1))
+    kw = dict(variant="fit", adapt_when=50, seed=5, thinning=5, burn_rows=3, lanes=lanes)
+    ref = SingleLevelSampler(2, pack, ids, 1.0, theta0, stage=False, block_threads=32, **kw)
+    want = ref.run(333).cpu().numpy()
+    s = SingleLevelSampler(2, pack, ids, 1.0, theta0, block_threads=block, **kw)
+    s.occupancy_hint = hint
+    got = s.run(333).cpu().numpy()
+    assert np.array_equal(got, want)
+    assert np.array_equal(s.state.cpu().numpy(), ref.state.cpu().numpy())
+    # and the five-dose / two-dose chains still follow the oracle
+    from pyhillfit_b200.sampler import variant_defaults
+    cov0, _, _ = variant_defaults("fit", theta0)
+    for k in (11, 22):
+        concs, y = table.concat(*use[ids[k]])
+        pb = ho.compute_pi_bit_of_log_likelihood(y)
+        lt0, l10 = c_oracle.log_target_batch(2, concs, y, theta0[k][None], 1.0, pb)
+        st = c_oracle.make_state(theta0[k], lt0[0], l10[0], cov0[k])
+        chain = c_oracle.am_single(2, concs, y, 1.0, pb, st, 0, 333, 5, 50, False, 5, k)
+        assert np.allclose(got[k], chain, rtol=1e-8, atol=1e-8)
+
+
+def test_empty_dataset_and_prior_only_agree(table):
+    """A dataset with no observations: the chain samples the prior (pi_bit = 0, no dose groups) exactly like a
+    temperature-0 chain of a real dataset with the same Philox ids."""
+    from pyhillfit_b200.packing import SinglePack
+    from pyhillfit_b200.sampler import SingleLevelSampler
+    pack = SinglePack([table.concat("Amiodarone", "hERG"), (np.zeros(0), np.zeros(0))])
+    assert list(pack.datasets["n_groups"]) == [4, 0]
+    theta0 = np.ones((4, 3))
+    a = SingleLevelSampler(2, pack, np.array([1, 1, 1, 1], dtype=np.int32), 1.0, theta0, variant="temp", seed=2, lanes=4)
+    b = SingleLevelSampler(2, pack, np.array([0, 0, 0, 0], dtype=np.int32), 0.0, theta0, variant="temp", seed=2, lanes=4)
+    ra, rb = a.run(500).cpu().numpy(), b.run(500).cpu().numpy()
+    assert np.allclose(ra, rb, rtol=1e-12, atol=1e-12) and np.all(np.isfinite(ra))
