@@ -10,7 +10,7 @@
  * compressed formulation.  Paths below are relative to /root/reference.
  *
  * Pinning: tests/test_oracle_golden.py compares every function here with
- * tests/golden/*.npz, which hold outputs of the unmodified reference executed in the build
+ * the .npz files under tests/golden, which hold outputs of the unmodified reference executed in the build
  * container through oracle/ref_shim.py (generator: oracle/gen_golden.py).
  *
  * Third-party arithmetic restated here:
