@@ -278,26 +278,35 @@ __global__ void __launch_bounds__(128, MINB)
     uint32_t row = t / cfg.thinning;
     cc.row_base = row + 1;
     cc.out = samples ? samples + (size_t)c * cfg.rows_capacity * (D + 1) : nullptr;
-    double gam_lane = 0.0;
+
+    // shared memory after the staged groups: [G > 1: one draw slot of D+1 doubles per thread][32 gamma_s per warp]
+    double *const slots = reinterpret_cast<double *>(smem_raw + (size_t)cfg.stage_groups * sizeof(phf_dose_group));
+    double *const gam_slots = slots + (G > 1 ? (size_t)blockDim.x * (D + 1) : 0) + (size_t)(threadIdx.x & ~31u);
 
     // The draws of an iteration depend on t only: once every G iterations lane gl prepares the draws of iteration
     // t + gl and parks them in its shared-memory slot; each iteration then reads its slot (a broadcast load: 2
-    // instructions instead of 8 shuffles, and no registers held across iterations).  (Unrolling the G iterations so
-    // that the draw computation shares a basic block with an iteration was measured: faster alone, slower when the
-    // model-1 and model-2 kernels share an SM -- two unrolled bodies no longer fit the 32 KB instruction cache.)
-    double *const slots = reinterpret_cast<double *>(smem_raw + (size_t)cfg.stage_groups * sizeof(phf_dose_group));
+    // instructions instead of 8 shuffles, and no registers held across iterations).  Measured / scheduled and
+    // rejected: unrolling the G iterations so that the draw computation shares a basic block with an iteration
+    // (faster alone, slower when the model-1 and model-2 kernels share an SM -- two unrolled bodies no longer fit
+    // the 32 KB instruction cache); the two lanes making one iteration's draws between them inside the iteration's
+    // own block (at 168 registers ptxas spills the Philox keys and the block gets longer, not shorter).
     double *const my_slot = slots + (size_t)threadIdx.x * (D + 1);
     const double *const chain_slots = slots + (size_t)(threadIdx.x & ~(unsigned)(G - 1)) * (D + 1);
     for (uint32_t it = 0; it < cfg.n_iters; ++it) {
         ++t;
         if ((it & 31u) == 0u) {
+            // gamma_s = 1/(s+1)**0.6, s = t - adapt_when (PyHillFit.py:841-842, PyHillTemp.py:117): a function of t
+            // only, so lane L computes it for iteration t + L once every 32 iterations and parks it in shared
+            // memory (a per-iteration broadcast LOAD instead of a shuffle: no shuffle point at the top of the loop)
             const uint32_t tl = t + lane;
-            // gamma_s = 1/(s+1)**0.6, s = t - adapt_when (PyHillFit.py:841-842, PyHillTemp.py:117)
-            gam_lane = tl > cfg.adapt_when
-                           ? fm::exp_clamped(T, -0.6 * fm::log_pos(T, (double)(tl - cfg.adapt_when) + 1.0))
-                           : 0.0;
+            const double gam_lane = tl > cfg.adapt_when
+                                        ? fm::exp_clamped(T, -0.6 * fm::log_pos(T, (double)(tl - cfg.adapt_when) + 1.0))
+                                        : 0.0;
+            __syncwarp();  // every lane has read the previous block's value
+            gam_slots[lane] = gam_lane;
+            __syncwarp();
         }
-        const double gam = __shfl_sync(0xffffffffu, gam_lane, it & 31u);
+        const double gam = gam_slots[it & 31u];
         Draws<D> dr;
         if (G == 1) {
             dr = make_draws<D>(T, cfg.seed, chain_id, t);
@@ -438,9 +447,10 @@ extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, dou
     if (block % 32 != 0 || block > 128)
         return set_error(PHF_EINVAL, "cfg.block_threads must be a multiple of 32, at most 128");
     if (cfg->stage_groups < 0) return set_error(PHF_EINVAL, "cfg.stage_groups must be >= 0");
-    // staged dose groups + (lanes > 1) one draw slot of d+1 doubles per thread
+    // staged dose groups + (lanes > 1) one draw slot of d+1 doubles per thread + 32 gamma_s per warp
     const size_t smem = (size_t)cfg->stage_groups * sizeof(phf_dose_group) +
-                        (lanes > 1 ? (size_t)block * ((cfg->model == 1 ? 2 : 3) + 1) * sizeof(double) : 0);
+                        (lanes > 1 ? (size_t)block * ((cfg->model == 1 ? 2 : 3) + 1) * sizeof(double) : 0) +
+                        (size_t)block * sizeof(double);
     if (smem > 200 * 1024) return set_error(PHF_EINVAL, "cfg.stage_groups needs more than 200 KB of shared memory");
     cudaStream_t s = (cudaStream_t)stream;
     const int minb = cfg->min_ctas_hint > 0 ? cfg->min_ctas_hint : 3;  // 168 registers: no spills; measured best at every size

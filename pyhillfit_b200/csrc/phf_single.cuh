@@ -69,6 +69,10 @@ PHF_DI double censored_pair(const double *T, double z0, double w0, double z1, do
 // Support (finite value) <=> pIC50 >= -3, 0 <= Hill <= 10, sigma > 1e-3; otherwise -inf like the reference:
 //   sigma <= 1e-3 -> likelihood -inf (doseresponse.py:212-214,238-240) and prior -inf (:306-308, log 0);
 //   pIC50 < -3 (:153-154) or Hill outside [0,10] (:181-182) -> prior -inf while the likelihood stays finite.
+//
+// G >= 2: there is ONE shuffle point (ptxas ends a basic block with a convergence check at every shuffle point, and
+// nothing is scheduled across it).  Lane 0 folds -n_other ln(sigma) - pi_bit into its partial of the likelihood sum,
+// lane 1 carries 4 ln(sigma - 1e-3) in the prior sum, so the two logarithms need no exchange of their own.
 template <int MODEL, int G, bool VOTE>
 PHF_DI void single_log_target_lanes(const double *T, const double *th, const phf_dose_group *__restrict__ grp, int ng,
                                     double pi_bit, double n_other_total, double temperature, int gl, unsigned mask,
@@ -81,17 +85,13 @@ PHF_DI void single_log_target_lanes(const double *T, const double *th, const phf
     const double sg = sigma_ok ? sigma : 1.0;
     const double inv_s = fm::rcp(sg);
     const double sm = sg - kSigmaLower;
-    double log_s, log_sm;
+    double log_s = 0.0, log_sm = 0.0, lane_log = 0.0;
     if (G >= 2) {
-        const double lv = fm::log_pos(T, gl == 0 ? sg : sm);
-        log_s = __shfl_sync(mask, lv, 0, G);
-        log_sm = __shfl_sync(mask, lv, 1, G);
+        lane_log = fm::log_pos(T, gl == 0 ? sg : sm);  // lane 0: ln sigma, lane 1: ln(sigma - 1e-3)
     } else {
         log_s = fm::log_pos(T, sg);
         log_sm = fm::log_pos(T, sm);
     }
-    // log_gamma_prior (doseresponse.py:308) + log_pic50_exponential (:156)
-    const double prior = fma(-kPic50ExpRate, pic50, fma(kSigmaShapeM1, log_sm, -sm * (1.0 / kSigmaScale)));
     bool in_support = sigma_ok && (pic50 >= kPic50ExpLower);
     if (MODEL == 2) in_support = in_support && (hill >= kHillLower) && (hill <= kHillUpper);
 
@@ -142,12 +142,20 @@ PHF_DI void single_log_target_lanes(const double *T, const double *th, const phf
         const phf_dose_group Gd = grp[g];
         dose_group_terms<MODEL>(T, Gd, hill, lic_hi, lic_lo, inv_ic50, inv_s, e2, cens);
     }
-    if (G >= 2) {
-        e2 = group_sum<G>(e2, mask);
-        cens = group_sum<G>(cens, mask);
-    }
     // cens - pi_bit - n_other ln(sigma) - e2 / (2 sigma^2)   (doseresponse.py:220-222, 246-248)
-    const double raw = fma(-e2, 0.5 * inv_s * inv_s, fma(-n_other_total, log_s, cens - pi_bit));
+    double raw, log_sm4;
+    if (G >= 2) {
+        double lik = fma(-e2, 0.5 * inv_s * inv_s, cens);
+        lik = gl == 0 ? fma(-n_other_total, lane_log, lik - pi_bit) : lik;
+        double pri = gl == 1 ? kSigmaShapeM1 * lane_log : 0.0;
+        raw = group_sum<G>(lik, mask);  // the shuffle point
+        log_sm4 = group_sum<G>(pri, mask);
+    } else {
+        raw = fma(-e2, 0.5 * inv_s * inv_s, fma(-n_other_total, log_s, cens - pi_bit));
+        log_sm4 = kSigmaShapeM1 * log_sm;
+    }
+    // log_gamma_prior (doseresponse.py:308) + log_pic50_exponential (:156)
+    const double prior = fma(-kPic50ExpRate, pic50, fma(-sm, 1.0 / kSigmaScale, log_sm4));
     loglik_t1 = sigma_ok ? raw : -CUDART_INF;
     const double post = temperature == 0.0 ? prior : fma(temperature, raw, prior);  // doseresponse.py:204-205,230-231
     log_target = in_support ? post : -CUDART_INF;
