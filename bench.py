@@ -259,6 +259,9 @@ def main():
     ap.add_argument("--ref-iters-per-step", type=int, default=4000)
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-segments", type=int, default=32)
+    ap.add_argument("--e2e-layout", default="row", choices=["row", "chain"],
+                    help="sample layout of the end-to-end call: row = [row][chain][d+1] (contiguous transfers)")
+    ap.add_argument("--layout", default="chain", choices=["row", "chain"], help="sample layout of the device-timed step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--block-threads", type=int, default=0)
@@ -304,7 +307,8 @@ def main():
                                co_resident_chains=0 if args.serial_models else len(wl[3 - model]["ids"]))
         s.occupancy_hint = args.occupancy_hint
         samplers[model] = s
-        buffers[model] = torch.empty((n, rows_per_step + 1, w["d"] + 1), dtype=torch.float64, device=dev)
+        buffers[model] = torch.empty((rows_per_step + 1, n, w["d"] + 1) if args.layout == "row" else
+                                     (n, rows_per_step + 1, w["d"] + 1), dtype=torch.float64, device=dev)
         streams[model] = torch.cuda.Stream(device=dev)
         n_chains += n
     flops_iter = sum(wl[m]["flops"] * len(wl[m]["ids"]) for m in (1, 2)) / n_chains
@@ -316,7 +320,7 @@ def main():
     def step():
         if args.serial_models:
             for model in (2, 1):
-                samplers[model].run(K, samples=buffers[model])
+                samplers[model].run(K, samples=buffers[model], row_major=args.layout == "row")
             return
         ev = torch.cuda.Event()
         ev.record(main_stream)
@@ -327,7 +331,7 @@ def main():
                 if stream_events is not None:   # per-launch duration on the launching stream
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a.record(st)
-                samplers[model].run(K, samples=buffers[model])
+                samplers[model].run(K, samples=buffers[model], row_major=args.layout == "row")
                 if stream_events is not None:
                     b.record(st)
                     stream_events[model].append((a, b))
@@ -377,7 +381,7 @@ def main():
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(dev)
         a.record(main_stream)
-        samplers[model].run(K, samples=buffers[model])
+        samplers[model].run(K, samples=buffers[model], row_major=args.layout == "row")
         b.record(main_stream)
         torch.cuda.synchronize(dev)
         kern_ms[model] = a.elapsed_time(b)
@@ -392,7 +396,8 @@ def main():
         for model in (1, 2):
             n = samplers[model].n
             pick = rng.choice(n, size=min(256, n), replace=False)
-            smp = buffers[model][torch.as_tensor(pick, device=dev)][:, :rows_per_step, :wl[model]["d"]].cpu().numpy()
+            by_chain = buffers[model].transpose(0, 1) if args.layout == "row" else buffers[model]
+            smp = by_chain[torch.as_tensor(pick, device=dev)][:, :rows_per_step, :wl[model]["d"]].cpu().numpy()
             per_row.append(np.mean([ess_min(c) for c in smp]) / rows_per_step)
         rows_per_s = value / thin
         ess_per_s = float(np.mean(per_row) * rows_per_s)
@@ -459,10 +464,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD % (args.chains_per_pair, thin), "chains_per_gpu": n_chains,
-                       "iters_per_step": K, "theta0": "host least-squares fit; chains 1..63 of a pair jittered by 2%",
+                       "iters_per_step": K, "sample_layout": args.layout + "-major", "theta0": "host least-squares fit; chains 1..63 of a pair jittered by 2%",
                        "l2": "each step writes %.2f GB of thinned samples (> 126 MB L2); chain state is register-"
                              "resident, packed data (54 KB) is staged in shared memory" %
-                             (sum(buffers[m][:, :rows_per_step].numel() for m in (1, 2)) * 8 / 1e9),
+                             (sum(buffers[m].numel() * rows_per_step // (rows_per_step + 1) for m in (1, 2)) * 8 / 1e9),
                        "data_source": "Crumb et al. dose-response table (tests/golden/datasets.npz), random-start chains",
                        "target_1e10_frac": value / world / 1e10},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
@@ -571,7 +576,8 @@ def run_e2e(args, torch, dev, pack, wl, samplers, rank, world, dist):
         n, d = len(w["ids"]), w["d"]
         st = torch.empty((n, _lib.state_size(d)), dtype=torch.float64).pin_memory()
         st.copy_(samplers[model].state.cpu())
-        smp = torch.empty((n, rows, d + 1), dtype=torch.float64).pin_memory()
+        # row-major samples: [row][chain][d+1], every segment is one contiguous device -> host transfer
+        smp = torch.empty((rows, n, d + 1) if args.e2e_layout == "row" else (n, rows, d + 1), dtype=torch.float64).pin_memory()
         ids = np.ascontiguousarray(w["ids"])
         temps = np.ones(n)
         jobs[model] = dict(n=n, state=st, samples=smp, ids=ids, temps=temps, t0=samplers[model].t)
@@ -583,7 +589,8 @@ def run_e2e(args, torch, dev, pack, wl, samplers, rank, world, dist):
         cfg = _lib.AmConfig(model=model, reset_mean_at_adapt=0, t0=j["t0"], n_iters=K, thinning=thin,
                             adapt_when=1000 * wl[model]["d"], burn_rows=0xFFFFFFFF, rows_capacity=rows, seed=25,
                             chain_id_base=(rank * 2 + (model - 1)) * (1 << 32), stage_groups=samplers[model].stage_groups,
-                            block_threads=samplers[model].block_threads, lanes_per_chain=samplers[model].lanes)
+                            block_threads=samplers[model].block_threads, lanes_per_chain=samplers[model].lanes,
+                            sample_layout=_lib.SAMPLES_ROW_MAJOR if args.e2e_layout == "row" else _lib.SAMPLES_CHAIN_MAJOR)
         rc = L.phf_am_single_run_host(C.byref(cfg), j["n"], j["state"].data_ptr(), j["ids"].ctypes.data,
                                       j["temps"].ctypes.data, pack.n_datasets, pack.datasets.ctypes.data,
                                       len(pack.groups), pack.groups.ctypes.data, j["samples"].data_ptr(),
@@ -614,7 +621,7 @@ def run_e2e(args, torch, dev, pack, wl, samplers, rank, world, dist):
         dt = float(tt.item())
     total = float(sum(j["n"] for j in jobs.values())) * K * args.e2e_steps * world
     return {"value": total / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "steps": args.e2e_steps, "api": "phf_am_single_run_host (pinned host buffers, %d overlapped segments/call)" % args.e2e_segments,
+            "steps": args.e2e_steps, "api": "phf_am_single_run_host (pinned host buffers, %s-major samples, %d overlapped segments/call)" % (args.e2e_layout, args.e2e_segments),
             "timing": "host wall clock around synchronous calls (each call ends with a stream synchronise)"}
 
 

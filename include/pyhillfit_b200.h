@@ -107,7 +107,16 @@ typedef struct phf_am_config {
     int32_t min_ctas_hint;       /* single-level only, 0: library default (3).  Register budget of the kernel variant,
                                     as the minimum number of 128-thread CTAs per SM it is compiled for: 2 -> 255
                                     registers, 3 -> 168, 4 -> 128, 6 -> 80.  A tuning knob; results do not depend on it. */
+    int32_t sample_layout;       /* single-level only.  PHF_SAMPLES_CHAIN_MAJOR (0): samples[chain][row][d+1], one chain's
+                                    rows contiguous (what np.savetxt of one chain wants).  PHF_SAMPLES_ROW_MAJOR (1):
+                                    samples[row][chain][d+1], one saved iteration of ALL chains contiguous: a warp's
+                                    write-out is one coalesced run and a block of rows is one contiguous region on the
+                                    device and on the host (phf_am_single_run_host copies it back with plain
+                                    contiguous transfers: 55 GB/s instead of 47 through the strided 2-D copy). */
+    int32_t reserved0;           /* must be 0 */
 } phf_am_config;
+#define PHF_SAMPLES_CHAIN_MAJOR 0
+#define PHF_SAMPLES_ROW_MAJOR 1
 
 /* Evaluate the target at theta0 and fill `state` (mean = theta0, cov = cov0, loga = 0, counters = 0). */
 int phf_am_single_init(int model, int64_t n_chains, const double *theta0 /* [n,d] */,
@@ -120,7 +129,8 @@ int phf_am_single_init(int model, int64_t n_chains, const double *theta0 /* [n,d
 int phf_am_single_lanes(int64_t n_chains);
 
 /*
- * Run cfg->n_iters iterations of every chain.  `samples` ([n_chains, rows_capacity, d+1], may be NULL)
+ * Run cfg->n_iters iterations of every chain.  `samples` ([n_chains, rows_capacity, d+1], or
+ * [rows_capacity, n_chains, d+1] with cfg->sample_layout = PHF_SAMPLES_ROW_MAJOR; may be NULL)
  * receives (theta, log_target) for each saved row of this call: local row = t/thinning - t0/thinning - 1.
  * Chains must be sorted by dataset_id when cfg->stage_groups > 0 (a CTA of B threads covers B / lanes chains).
  */

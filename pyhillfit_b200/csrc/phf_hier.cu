@@ -435,6 +435,8 @@ extern "C" int phf_am_hier_run(const phf_am_config *cfg, int32_t n_expts, int64_
     if (!cfg || !priors) return set_error(PHF_EINVAL, "phf_am_hier_run: cfg/priors is NULL");
     if (n_expts < 1 || n_expts > PHF_HIER_BIG_MAX_EXPTS) return set_error(PHF_ENOTSUP, "n_expts outside 1..128");
     if (cfg->thinning == 0) return set_error(PHF_EINVAL, "cfg.thinning must be >= 1");
+    if (cfg->sample_layout != PHF_SAMPLES_CHAIN_MAJOR)
+        return set_error(PHF_ENOTSUP, "phf_am_hier_run: samples are chain-major (cfg.sample_layout must be 0)");
     if (n_chains < 0 || (n_chains > 0 && (!state || !dataset_id || !datasets || !points)))
         return set_error(PHF_EINVAL, "phf_am_hier_run: null pointer");
     if ((uint64_t)cfg->t0 + cfg->n_iters > 0xFFFFFFFFull) return set_error(PHF_EINVAL, "iteration counter overflow");

@@ -44,6 +44,8 @@ extern "C" int phf_am_single_run_host(const phf_am_config *cfg, int64_t n_chains
     if (!cfg) return set_error(PHF_EINVAL, "phf_am_single_run_host: cfg is NULL");
     if (cfg->model != 1 && cfg->model != 2) return set_error(PHF_EINVAL, "cfg.model must be 1 or 2");
     if (cfg->thinning == 0) return set_error(PHF_EINVAL, "cfg.thinning must be >= 1");
+    if (cfg->sample_layout != PHF_SAMPLES_CHAIN_MAJOR && cfg->sample_layout != PHF_SAMPLES_ROW_MAJOR)
+        return set_error(PHF_EINVAL, "cfg.sample_layout must be PHF_SAMPLES_CHAIN_MAJOR or PHF_SAMPLES_ROW_MAJOR");
     if (device < 0 || device >= 16) return set_error(PHF_EINVAL, "device index outside 0..15");
     if (n_chains <= 0 || n_datasets <= 0 || n_groups <= 0 || !state || !dataset_id || !temperature || !datasets ||
         !groups)
@@ -108,11 +110,17 @@ extern "C" int phf_am_single_run_host(const phf_am_config *cfg, int64_t n_chains
         if (samples && rows > 0) {
             cudaEventRecord(w.done[b], cs);
             cudaStreamWaitEvent(w.copy, w.done[b], 0);
-            // device [chain][seg_rows_cap][d+1] -> host [chain][rows_capacity][d+1] at row offset rows_done
-            e = cudaMemcpy2DAsync(samples + (size_t)rows_done * (d + 1), (size_t)cfg->rows_capacity * row_bytes,
-                                  w.samples[b].p, (size_t)seg_rows_cap * row_bytes, (size_t)rows * row_bytes,
-                                  (size_t)n_chains, cudaMemcpyDeviceToHost, w.copy);
-            if (e) { rc = set_cuda_error(e, "cudaMemcpy2DAsync"); break; }
+            if (cfg->sample_layout == PHF_SAMPLES_ROW_MAJOR) {
+                // device [seg_rows_cap][chain][d+1] -> host [rows_capacity][chain][d+1] at row rows_done: contiguous
+                e = cudaMemcpyAsync(samples + (size_t)rows_done * n_chains * (d + 1), w.samples[b].p,
+                                    (size_t)rows * n_chains * row_bytes, cudaMemcpyDeviceToHost, w.copy);
+            } else {
+                // device [chain][seg_rows_cap][d+1] -> host [chain][rows_capacity][d+1] at row offset rows_done
+                e = cudaMemcpy2DAsync(samples + (size_t)rows_done * (d + 1), (size_t)cfg->rows_capacity * row_bytes,
+                                      w.samples[b].p, (size_t)seg_rows_cap * row_bytes, (size_t)rows * row_bytes,
+                                      (size_t)n_chains, cudaMemcpyDeviceToHost, w.copy);
+            }
+            if (e) { rc = set_cuda_error(e, "cudaMemcpyAsync(samples)"); break; }
             cudaEventRecord(w.copied[b], w.copy);
         }
         done_iters += c.n_iters;

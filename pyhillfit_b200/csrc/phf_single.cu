@@ -121,7 +121,8 @@ struct ChainConst {
     double pi_bit, n_other_total, temp;
     uint32_t thinning, adapt_when, burn_rows, row_base;
     int reset_mean;
-    double *out;  // this chain's rows of the samples buffer, or nullptr
+    double *out;        // this chain's first row in the samples buffer, or nullptr
+    size_t row_stride;  // doubles between two rows of the chain
     bool active;
 };
 
@@ -190,7 +191,7 @@ PHF_DI void am_step(const double *T, const ChainConst &cc, ChainRegs<MODEL> &s, 
         until_save = cc.thinning;
         ++row;
         if (cc.out && cc.active) {
-            double *o = cc.out + (size_t)(row - cc.row_base) * (D + 1);
+            double *o = cc.out + (size_t)(row - cc.row_base) * cc.row_stride;
             // the G lanes of the chain write the row's D+1 columns between them
 #pragma unroll
             for (int k = 0; k <= D; ++k)
@@ -277,7 +278,10 @@ __global__ void __launch_bounds__(128, MINB)
     uint32_t until_save = cfg.thinning - (t % cfg.thinning);
     uint32_t row = t / cfg.thinning;
     cc.row_base = row + 1;
-    cc.out = samples ? samples + (size_t)c * cfg.rows_capacity * (D + 1) : nullptr;
+    // chain-major: rows of a chain D+1 doubles apart; row-major: n chains apart (phf_am_config.sample_layout)
+    const bool row_major = cfg.sample_layout == PHF_SAMPLES_ROW_MAJOR;
+    cc.out = samples ? samples + (row_major ? (size_t)c : (size_t)c * cfg.rows_capacity) * (D + 1) : nullptr;
+    cc.row_stride = row_major ? (size_t)n * (D + 1) : (size_t)(D + 1);
 
     // shared memory after the staged groups: [G > 1: one draw slot of D+1 doubles per thread][32 gamma_s per warp]
     double *const slots = reinterpret_cast<double *>(smem_raw + (size_t)cfg.stage_groups * sizeof(phf_dose_group));
@@ -430,6 +434,8 @@ extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, dou
     if (!cfg) return set_error(PHF_EINVAL, "phf_am_single_run: cfg is NULL");
     if (cfg->model != 1 && cfg->model != 2) return set_error(PHF_EINVAL, "cfg.model must be 1 or 2");
     if (cfg->thinning == 0) return set_error(PHF_EINVAL, "cfg.thinning must be >= 1");
+    if (cfg->sample_layout != PHF_SAMPLES_CHAIN_MAJOR && cfg->sample_layout != PHF_SAMPLES_ROW_MAJOR)
+        return set_error(PHF_EINVAL, "cfg.sample_layout must be PHF_SAMPLES_CHAIN_MAJOR or PHF_SAMPLES_ROW_MAJOR");
     if (n_chains < 0 || (n_chains > 0 && (!state || !dataset_id || !temperature || !datasets || !groups)))
         return set_error(PHF_EINVAL, "phf_am_single_run: null pointer");
     if ((uint64_t)cfg->t0 + cfg->n_iters > 0xFFFFFFFFull) return set_error(PHF_EINVAL, "iteration counter overflow");

@@ -75,8 +75,9 @@ class _Base:
     def rows_for(self, n_iters):
         return (self.t + n_iters) // self.thinning - self.t // self.thinning
 
-    def _config(self, n_iters, rows_capacity):
-        return _lib.AmConfig(model=getattr(self, "model", 0), reset_mean_at_adapt=int(self.reset_mean), t0=self.t,
+    def _config(self, n_iters, rows_capacity, row_major=False):
+        return _lib.AmConfig(sample_layout=_lib.SAMPLES_ROW_MAJOR if row_major else _lib.SAMPLES_CHAIN_MAJOR,
+                             model=getattr(self, "model", 0), reset_mean_at_adapt=int(self.reset_mean), t0=self.t,
                              n_iters=int(n_iters), thinning=self.thinning, adapt_when=int(self.adapt_when),
                              burn_rows=int(self.burn_rows), rows_capacity=int(rows_capacity), seed=int(self.seed),
                              chain_id_base=int(self.chain_id_base), stage_groups=int(self.stage_groups),
@@ -159,18 +160,22 @@ class SingleLevelSampler(_Base):
         """[n, d+1] row 0 of every chain: (theta0, log_target(theta0)) -- call before run()."""
         return self.state[:, :self.d + 1].clone()
 
-    def run(self, n_iters, samples=None, keep=True):
-        """Advance every chain by n_iters.  Returns the [n, rows, d+1] device tensor of rows saved by this call
-        (a view of `samples` if given), or None when keep=False (thermodynamic-integration-only runs)."""
+    def run(self, n_iters, samples=None, keep=True, row_major=False):
+        """Advance every chain by n_iters.  Returns the device tensor of rows saved by this call (a view of `samples`
+        if given): [n, rows, d+1], or [rows, n, d+1] with row_major=True (one saved iteration of all chains
+        contiguous: coalesced write-out, contiguous transfers); None when keep=False (thermodynamic-integration-only
+        runs)."""
         torch = self.torch
         rows = self.rows_for(n_iters)
         cap = rows
+        ax_n, ax_r = (1, 0) if row_major else (0, 1)
         if keep:
             if samples is None:
-                samples = torch.empty((self.n, max(rows, 1), self.d + 1), dtype=torch.float64, device=self.device)
-            cap = samples.shape[1]
-            assert samples.shape[0] == self.n and samples.shape[2] == self.d + 1 and samples.is_contiguous()
-        cfg = self._config(n_iters, cap)
+                shape = (max(rows, 1), self.n, self.d + 1) if row_major else (self.n, max(rows, 1), self.d + 1)
+                samples = torch.empty(shape, dtype=torch.float64, device=self.device)
+            cap = samples.shape[ax_r]
+            assert samples.shape[ax_n] == self.n and samples.shape[2] == self.d + 1 and samples.is_contiguous()
+        cfg = self._config(n_iters, cap, row_major)
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().phf_am_single_run(C.byref(cfg), self.n, self.state.data_ptr(),
                                                      self.dataset_id.data_ptr(), self.temperature.data_ptr(),
@@ -178,7 +183,9 @@ class SingleLevelSampler(_Base):
                                                      samples.data_ptr() if keep else None,
                                                      _lib.current_stream_ptr()), "phf_am_single_run")
         self.t += int(n_iters)
-        return samples[:, :rows] if keep else None
+        if not keep:
+            return None
+        return samples[:rows] if row_major else samples[:, :rows]
 
     def loglik_t1_mean(self):
         """Mean over counted rows of the temperature-1 log-likelihood (compute_bayes_factors.py:11-27)."""

@@ -9,3 +9,13 @@ import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('bench value %.4e  ms/step %.3f  roofline %.3f  kernel_ms %s' % (d['value'], d['ms_per_step'], d['roofline']['frac'], d.get('kernel_ms')))
 "
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-other-configs --layout row --e2e-layout row 2>>gpurun_out/err.txt | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('row-major: bench value %.4e  ms/step %.3f  e2e %.4e' % (d['value'], d['ms_per_step'], d['e2e']['value']))
+"
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-other-configs --e2e-layout chain 2>>gpurun_out/err.txt | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('chain-major: bench value %.4e  ms/step %.3f  e2e %.4e' % (d['value'], d['ms_per_step'], d['e2e']['value']))
+"

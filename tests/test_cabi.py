@@ -55,9 +55,9 @@ def test_struct_layouts_match_the_header(tmp_path):
 int main(void) {
     printf("%zu %zu %zu %zu %zu %zu\n", sizeof(phf_dose_group), sizeof(phf_dataset), sizeof(phf_hier_point),
            sizeof(phf_hier_dataset), sizeof(phf_am_config), sizeof(phf_hier_priors));
-    printf("%zu %zu %zu %zu %zu\n", offsetof(phf_am_config, seed), offsetof(phf_am_config, chain_id_base),
+    printf("%zu %zu %zu %zu %zu %zu\n", offsetof(phf_am_config, seed), offsetof(phf_am_config, chain_id_base),
            offsetof(phf_am_config, stage_groups), offsetof(phf_am_config, lanes_per_chain),
-           offsetof(phf_dataset, pi_bit));
+           offsetof(phf_dataset, pi_bit), offsetof(phf_am_config, sample_layout));
     printf("%d %d %d\n", PHF_STATE_SIZE(2), PHF_STATE_SIZE(3), PHF_STATE_SIZE(11));
     return 0;
 }
@@ -70,7 +70,8 @@ int main(void) {
                      _lib.HIER_DATASET_DTYPE.itemsize, C.sizeof(_lib.AmConfig), C.sizeof(_lib.HierPriors)]
     offs = [int(x) for x in out[1].split()]
     assert offs == [_lib.AmConfig.seed.offset, _lib.AmConfig.chain_id_base.offset, _lib.AmConfig.stage_groups.offset,
-                    _lib.AmConfig.lanes_per_chain.offset, _lib.DATASET_DTYPE.fields["pi_bit"][1]]
+                    _lib.AmConfig.lanes_per_chain.offset, _lib.DATASET_DTYPE.fields["pi_bit"][1],
+                    _lib.AmConfig.sample_layout.offset]
     assert [int(x) for x in out[2].split()] == [_lib.state_size(2), _lib.state_size(3), _lib.state_size(11)]
 
 

@@ -118,6 +118,35 @@ def test_host_buffer_entry_point(table):
                "phf_am_single_run_host")
     assert np.array_equal(samples, want)
     assert np.array_equal(state, ref.state.cpu().numpy())
+    # row-major samples ([row][chain][d+1]: contiguous segment transfers): the same numbers, transposed
+    state_r = torch.from_numpy(state0.copy()).pin_memory().numpy()
+    samples_r = torch.empty((rows, len(ids), 4), dtype=torch.float64).pin_memory().numpy()
+    cfg.sample_layout = _lib.SAMPLES_ROW_MAJOR
+    _lib.check(L.phf_am_single_run_host(C.byref(cfg), len(ids), state_r.ctypes.data, ids.ctypes.data,
+                                        temps.ctypes.data, pack.n_datasets, pack.datasets.ctypes.data,
+                                        len(pack.groups), pack.groups.ctypes.data, samples_r.ctypes.data, 7, 0),
+               "phf_am_single_run_host")
+    assert np.array_equal(samples_r.transpose(1, 0, 2), want)
+    assert np.array_equal(state_r, state)
+
+
+@pytest.mark.parametrize("model,lanes", [(2, 1), (2, 2), (1, 4)])
+def test_row_major_samples_are_the_transpose(table, model, lanes):
+    """cfg.sample_layout = PHF_SAMPLES_ROW_MAJOR changes where rows land, nothing else (device-pointer path, segmented)."""
+    from pyhillfit_b200.packing import SinglePack
+    from pyhillfit_b200.sampler import SingleLevelSampler
+    pack = SinglePack([table.concat(d, c) for d, c in table.pairs()[:5]])
+    ids = np.repeat(np.arange(5, dtype=np.int32), 13)   # 65 chains: a ragged last warp
+    d = 2 if model == 1 else 3
+    theta0 = np.tile([5.5, 1.0, 6.0] if model == 2 else [5.5, 6.0], (len(ids), 1))
+    kw = dict(variant="fit", adapt_when=100, seed=3, thinning=4, lanes=lanes)
+    a = SingleLevelSampler(model, pack, ids, 1.0, theta0, **kw)
+    b = SingleLevelSampler(model, pack, ids, 1.0, theta0, **kw)
+    want = a.run(600).cpu().numpy()
+    got = np.concatenate([b.run(250, row_major=True).cpu().numpy(), b.run(350, row_major=True).cpu().numpy()])
+    assert got.shape == (150, len(ids), d + 1)
+    assert np.array_equal(got.transpose(1, 0, 2), want)
+    assert np.array_equal(a.state.cpu().numpy(), b.state.cpu().numpy())
 
 
 def test_hier_trajectories_follow_oracle(table):
