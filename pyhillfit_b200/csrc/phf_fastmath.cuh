@@ -234,11 +234,12 @@ PHF_FM double log_pos(const double *T, double x)
     return fma(ef, kLn2Hi, fma(2.0, f, tail));
 }
 
-// ---- erfcx(t) = exp(t^2) erfc(t), t >= 0 ----------------------------------------------------------
+// ---- erfcx(t) = exp(t^2) erfc(t), 0 <= t <= 1e140 --------------------------------------------------
 // erfcx(t) (1 + 2t) = P(q), q = (t - K)/(t + K): one polynomial on q in [-1, 1) covers the half line.
+// (Every caller passes t = |response - bound| / (sigma sqrt 2) with sigma > 1e-3: t < 1e5.  Beyond 1e140 the
+// product a b below overflows; a clamp would cost 8 instructions per call.)
 PHF_FM double erfcx_nonneg(const double *T, double t)
 {
-    t = fmin(t, 1e140);
     const double a = t + PHF_ERFCX_K, b = fma(2.0, t, 1.0);
     const double r = rcp(a * b);
     const double q = (t - PHF_ERFCX_K) * (r * b);

@@ -133,12 +133,15 @@ PHF_DI void ln_ic50(double pic50, double &hi, double &lo)
 }
 
 // (dose/IC50)^hill = exp(hill * (ln dose - ln IC50)) -- python/doseresponse.py:84-85.
-// 0^0 = inf^0 = 1 as numpy's power does.
+// ZERO_POW: 0^0 = inf^0 = 1 as numpy's power does (a zero dose with Hill exactly 0: 0 * -inf is NaN).  The log-target
+// entry points keep the check; inside the samplers a proposal's Hill is a continuous draw and exp(0 * L) is 1 for
+// every finite L anyway, so they leave the three instructions per dose out.
+template <bool ZERO_POW = true>
 PHF_DI double hill_ratio_pow(const double *T, double lnc_hi, double lnc_lo, double lic_hi, double lic_lo, double hill)
 {
     const double L = (lnc_hi - lic_hi) + (lnc_lo - lic_lo);
     const double x = fm::exp_clamped(T, hill * L);  // saturates at e^+-700, where the response is 100 / 0 to the last bit
-    return hill == 0.0 ? 1.0 : x;
+    return (ZERO_POW && hill == 0.0) ? 1.0 : x;
 }
 
 // predicted response 100 (1 - 1/(1 + x)) -- python/doseresponse.py:85

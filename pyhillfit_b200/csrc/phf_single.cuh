@@ -110,7 +110,8 @@ PHF_DI void single_log_target_lanes(const double *T, const double *th, const phf
         const int g = gl + u * G;
         const bool on = g < ng;
         const phf_dose_group *Gp = grp + (on ? g : 0);
-        const double x = MODEL == 2 ? hill_ratio_pow(T, Gp->lnc_hi, Gp->lnc_lo, lic_hi, lic_lo, hill)
+        // (VOTE marks the sampler kernels: see hill_ratio_pow for what they skip)
+        const double x = MODEL == 2 ? hill_ratio_pow<!VOTE>(T, Gp->lnc_hi, Gp->lnc_lo, lic_hi, lic_lo, hill)
                                     : Gp->conc * inv_ic50;
         const double p = hill_response(x);
         const double r = Gp->ybar - p;
