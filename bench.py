@@ -70,7 +70,7 @@ def flops_per_iteration(model, groups):
 # ----------------------------------------------------------------------------------------------
 def build_workload(chains_per_pair):
     from _data import Table
-    from pyhillfit_b200.initial_fit import best_fit
+    from pyhillfit_b200.initial_fit import best_fit_batch
     from pyhillfit_b200.packing import SinglePack
     table = Table("crumb_data")
     pairs = table.pairs()
@@ -80,7 +80,7 @@ def build_workload(chains_per_pair):
     out = {}
     for model in (1, 2):
         d = 2 if model == 1 else 3
-        fits = np.stack([best_fit(model, *xy)[0] for xy in data])
+        fits = best_fit_batch(model, data)[0]
         theta0 = np.repeat(fits, chains_per_pair, axis=0)
         jitter = 1.0 + 0.02 * rng.standard_normal(theta0.shape)
         jitter[::chains_per_pair] = 1.0  # chain 0 of every pair starts exactly at the least-squares fit

@@ -213,6 +213,13 @@ int phf_am_single_run_host(const phf_am_config *cfg, int64_t n_chains, double *s
 int phf_write_rows_text_host(const char *path, const char *header, const double *data, int64_t n_rows, int32_t n_cols,
                              int64_t row_stride, int32_t append, int32_t n_threads);
 
+/* The writer's number formatter on its own: the bytes of "%.18e" (19 significant digits, correctly rounded, what
+ * np.savetxt writes) into buf (>= 32 bytes), returns the length; exact 128-bit integer arithmetic for
+ * 1e-9 <= |v| < 1e19, the C library otherwise.  phf_format_e18_mismatches counts the values of data[0..n) whose
+ * bytes differ from the C library's (the self-check tests/test_host_logic.py runs on 2e7 doubles). */
+int phf_format_e18(double v, char *buf);
+int64_t phf_format_e18_mismatches(const double *data, int64_t n);
+
 /* ------------------------------------------------------------------------------------------------
  * Utilities
  * ---------------------------------------------------------------------------------------------- */

@@ -58,12 +58,13 @@ def run_single_level(dr, args, pairs):
     """python/PyHillFit.py:645-867 for all pairs at once."""
     import torch
     from . import chainio
-    from .initial_fit import best_fit
+    from .initial_fit import best_fit_batch
     from .packing import SinglePack
     from .sampler import SingleLevelSampler
     temperature = 1
     assert args.iterations % args.thinning == 0            # PyHillFit.py:805
     jobs, data = [], []
+    t_phase = time.time()
     for drug, channel in pairs:
         try:
             num_expts, experiment_numbers, experiments = dr.load_crumb_data(drug, channel)
@@ -75,13 +76,17 @@ def run_single_level(dr, args, pairs):
         if np.any(np.isnan(responses)):
             print("Skipping {} because of empty responses / missing data".format((drug, channel)))
             continue
-        theta0, ss = best_fit(args.model, concs, responses)
-        chainio.save_best_fit_params(images_dir, cdrug, cchannel, args.model, theta0)
-        jobs.append(dict(drug=cdrug, channel=cchannel, chain_file=chain_file, theta0=theta0))
+        jobs.append(dict(drug=cdrug, channel=cchannel, chain_file=chain_file, images_dir=images_dir))
         data.append((concs, responses))
+    fits, _ = best_fit_batch(args.model, data)               # least-squares starts of all pairs at once
+    for job, theta0 in zip(jobs, fits):
+        job["theta0"] = theta0
+        chainio.save_best_fit_params(job["images_dir"], job["drug"], job["channel"], args.model, theta0)
     if args.best_fit_only or not jobs:
         return jobs
     R = args.num_chains
+    print("data + least-squares starts of {} pairs: {:.2f} s".format(len(jobs), time.time() - t_phase))
+    t_phase = time.time()
     pack = SinglePack(data)
     ids = np.repeat(np.arange(len(jobs), dtype=np.int32), R)
     theta0 = np.repeat(np.stack([j["theta0"] for j in jobs]), R, axis=0)
@@ -97,6 +102,8 @@ def run_single_level(dr, args, pairs):
     d = s.d
     chain = torch.empty((s.n, saved_iterations, d + 1), dtype=torch.float64, device=s.device)
     chain[:, 0, :] = s.initial_row()
+    torch.cuda.synchronize()
+    print("packing, CUDA start-up, sampler state: {:.2f} s".format(time.time() - t_phase))
     start = time.time()
     done = 0
     while done < args.iterations:
@@ -107,24 +114,27 @@ def run_single_level(dr, args, pairs):
         done += k
     torch.cuda.synchronize()
     print("\n{} chains x {} iterations in {:.2f} s on the GPU\n".format(s.n, args.iterations, time.time() - start))
+    t_phase = time.time()
     host = chain[:, burn:, :].cpu().numpy()                 # remove burn-in before saving (PyHillFit.py:861-864)
+    print("chains to the host: {:.2f} s".format(time.time() - t_phase))
+    t_phase = time.time()
     for j, job in enumerate(jobs):
         for r in range(R):
             f = job["chain_file"] if r == 0 else chainio.extra_chain_name(job["chain_file"], r)
             chainio.save_single_level_chain(f, host[j * R + r], job["drug"], job["channel"])
         print("\n\n{} + {} complete!\n\n".format(job["drug"], job["channel"]))
+    print("chain files: {:.2f} s".format(time.time() - t_phase))
     return jobs
 
 
-def hierarchical_start(experiments, locs):
-    """theta0 of python/PyHillFit.py:243-257, 303-336 with the least-squares initialiser in place of CMA-ES."""
+def hierarchical_start(experiments, locs, best_fits=None):
+    """theta0 of python/PyHillFit.py:243-257, 303-336 with the least-squares initialiser in place of CMA-ES.
+    best_fits: the per-experiment fits [Ne, 3] if the caller already made them (all pairs in one batch)."""
     import scipy.stats as st
     from scipy.optimize import minimize
-    from .initial_fit import best_fit
-    best_fits = []
-    for e in experiments:
-        th, ss = best_fit(2, e[:, 0], e[:, 1], pic50_lower=-2.0)
-        best_fits.append(th)
+    from .initial_fit import best_fit_batch
+    if best_fits is None:
+        best_fits, _ = best_fit_batch(2, [(e[:, 0], e[:, 1]) for e in experiments], pic50_lower=-2.0)
     best_fits = np.array(best_fits)
     sigma_cur = np.mean(best_fits[:, -1])
     if sigma_cur <= locs[3]:
@@ -169,10 +179,16 @@ def run_hierarchical(dr, args, pairs):
             print("You've asked to fit to an impossible number of experiments for {} + {}\n".format(drug, channel))
             print("Therefore proceeding with all experiments in the input data file\n")
         cdrug, cchannel, output_dir, chain_dir, figs_dir, chain_file = dr.hierarchical_output_dirs_and_chain_file(drug, channel, num_expts)
-        theta0 = hierarchical_start(experiments, locs)
-        print("first mcmc iteration:\n", theta0)
-        jobs.append(dict(drug=cdrug, channel=cchannel, chain_file=chain_file, experiments=experiments, theta0=theta0,
+        jobs.append(dict(drug=cdrug, channel=cchannel, chain_file=chain_file, experiments=experiments,
                          ne=len(experiments)))
+    # per-experiment least-squares fits of every pair in one batch (704 fits for the Crumb table)
+    from .initial_fit import best_fit_batch
+    all_fits, _ = best_fit_batch(2, [(e[:, 0], e[:, 1]) for j in jobs for e in j["experiments"]], pic50_lower=-2.0)
+    at = 0
+    for job in jobs:
+        job["theta0"] = hierarchical_start(job["experiments"], locs, all_fits[at:at + job["ne"]])
+        at += job["ne"]
+        print("first mcmc iteration:\n", job["theta0"])
     saved_iterations = args.iterations // args.thinning + 1
     burn = saved_iterations // 4                              # PyHillFit.py:472
     R = args.num_chains
@@ -214,10 +230,12 @@ def main(argv=None):
         parser.print_help()
         return 1
     args = parser.parse_args(argv)
+    t_import = time.time()
     from . import doseresponse as dr
     dr.define_model(args.model)
     dr.setup(args.data_file)
     pairs = select_pairs(dr, args)
+    print("imports + reading {}: {:.2f} s".format(args.data_file, time.time() - t_import))
     if args.hierarchical:
         run_hierarchical(dr, args, pairs)
     else:

@@ -48,7 +48,7 @@ assert HIER_POINT_DTYPE.itemsize == 32 and HIER_DATASET_DTYPE.itemsize == 16
 
 EXPORTS = ["phf_log_target_batch", "phf_am_single_init", "phf_am_single_run", "phf_am_single_lanes", "phf_hier_log_target_batch",
            "phf_am_hier_init", "phf_am_hier_run", "phf_am_single_run_host", "phf_write_rows_text_host",
-           "phf_hier_predictive_cdfs", "phf_version", "phf_last_error",
+           "phf_hier_predictive_cdfs", "phf_format_e18", "phf_format_e18_mismatches", "phf_version", "phf_last_error",
            "phf_fp64_peak_probe", "phf_launch_count"]
 
 _lib = None
@@ -86,6 +86,9 @@ def load():
                                            C.c_double, _p, _p]
     L.phf_write_rows_text_host.argtypes = [C.c_char_p, C.c_char_p, _p, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
                                            C.c_int32]
+    L.phf_format_e18.argtypes = [C.c_double, C.c_char_p]
+    L.phf_format_e18_mismatches.argtypes = [_p, C.c_int64]
+    L.phf_format_e18_mismatches.restype = C.c_int64
     for name in EXPORTS:
         f = getattr(L, name)
         if f.restype is C.c_int and name not in ("phf_version",):

@@ -87,8 +87,21 @@ def list_drug_channel_options(args_all):
     return drugs_to_run, channels_to_run
 
 
+_pair_rows = (None, None)   # (the DataFrame the index was built for, {(drug, channel): its rows})
+
+
+def _rows_of(drug, channel):
+    """df[(df.Drug == drug) & (df.Channel == channel)] (:59) without re-scanning the table for every pair: the rows
+    of each (drug, channel) are looked up in an index built once per DataFrame (same rows, same order)."""
+    global _pair_rows
+    if _pair_rows[0] is not df:
+        _pair_rows = (df, {key: rows for key, rows in df.groupby(['Drug', 'Channel'], sort=False)})
+    rows = _pair_rows[1].get((drug, channel))
+    return rows if rows is not None else df[(df['Drug'] == drug) & (df['Channel'] == channel)]
+
+
 def load_crumb_data(drug, channel):
-    sel = df[(df['Drug'] == drug) & (df['Channel'] == channel)]
+    sel = _rows_of(drug, channel)
     experiment_numbers = np.array(sel.Experiment.unique())
     num_expts = max(experiment_numbers)
     experiments = [np.array(sel[sel['Experiment'] == expt][['Concentration', 'Inhibition']], dtype=float)

@@ -247,3 +247,61 @@ def test_native_text_writer_is_byte_identical_to_savetxt(tmp_path):
     assert open(ours, "rb").read() == b""
     with pytest.raises(_lib.PhfError):
         _lib.write_rows_text(str(tmp_path / "no_such_dir" / "x.txt"), a[:2])
+
+
+def test_e18_formatter_is_exact():
+    """The writer's own "%.18e" (128-bit integer arithmetic for 1e-9 <= |v| < 1e19, C library elsewhere): the same
+    bytes as Python's formatting on hand-picked and random values, and as the C library's on 6e6 doubles -- chain-like
+    magnitudes, every binade, short decimals, exact ties (integers and halves need rounding to even at 19 digits only
+    beyond 2^63, dyadic fractions have exact decimal expansions), neighbours of every power of ten."""
+    import ctypes as C
+    from pyhillfit_b200 import _lib
+    L = _lib.load()
+    buf = C.create_string_buffer(64)
+
+    def ours(v):
+        n = L.phf_format_e18(float(v), buf)
+        return buf.raw[:n].decode()
+
+    rng = np.random.default_rng(1)
+    picked = [0.0, -0.0, 1.0, -1.0, 0.1, 1 / 3, 5.5, 1e-9, np.nextafter(1e-9, 0), 1e19, np.nextafter(1e19, 0), 1e18,
+              9.999999999999999e-10, 99.99999999999999, -58.39140921642633, 2.0 ** -30, 2.0 ** 63, 2.0 ** 64,
+              np.inf, -np.inf, np.nan, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, 1e300, 1e-300,
+              123456.789, 0.5, 0.25, 0.125, 9.5, 1e15 + 0.5, 4503599627370496.5, 9007199254740993.0]
+    picked += [float(v) for v in np.concatenate([10.0 ** np.arange(-12, 22), np.nextafter(10.0 ** np.arange(-12, 22), 0),
+                                                 np.nextafter(10.0 ** np.arange(-12, 22), np.inf)])]
+    picked += [float(v) for v in rng.normal(0, 40, 20000)]
+    picked += [float(v) for v in np.exp(rng.uniform(-25, 45, 20000)) * rng.choice([-1, 1], 20000)]
+    for v in picked:
+        assert ours(v) == "%.18e" % v, v
+    for x in (np.ldexp(rng.uniform(0.5, 1, 2_000_000), rng.integers(-40, 70, 2_000_000)),
+              rng.normal(0, 50, 1_000_000),
+              np.round(rng.uniform(-1000, 1000, 1_000_000), rng.integers(0, 6)),
+              rng.integers(-10 ** 9, 10 ** 9, 1_000_000) / 2.0,
+              np.ldexp(rng.uniform(0.5, 1, 1_000_000), rng.integers(-1074, 1024, 1_000_000))):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert L.phf_format_e18_mismatches(x.ctypes.data, len(x)) == 0
+
+
+def test_batched_initial_fit_matches_the_scalar_one(table):
+    """best_fit_batch (all datasets per numpy call, Nelder-Mead under a mask) reaches the scalar best_fit's minimum:
+    the same sum of squares to 1e-9 relative, the same parameters wherever the minimum is not flat, for both
+    models, ragged dataset sizes and the hierarchical start's per-experiment fits (pIC50 lower bound -2)."""
+    from pyhillfit_b200.initial_fit import best_fit, best_fit_batch
+    pairs = table.pairs()[::7]
+    data = [table.concat(*p) for p in pairs]
+    assert len({len(c) for c, _ in data}) > 1
+    for model in (1, 2):
+        th, ss = best_fit_batch(model, data)
+        for k, (c, y) in enumerate(data):
+            rt, rs = best_fit(model, c, y)
+            assert ss[k] <= rs * (1 + 1e-9) + 1e-9 and ss[k] >= rs * (1 - 1e-6) - 1e-9
+            if np.max(np.abs(th[k] - rt)) > 1e-4:          # a flat direction: both are minima of the same height
+                assert abs(ss[k] - rs) <= 1e-6 * max(rs, 1.0)
+            assert th[k, -1] == pytest.approx(max(np.sqrt(ss[k] / len(c)), 2e-3))
+    ex = [e for p in pairs[:6] for e in table.experiments(*p)]
+    th, ss = best_fit_batch(2, [(e[:, 0], e[:, 1]) for e in ex], pic50_lower=-2.0)
+    for k, e in enumerate(ex):
+        rt, rs = best_fit(2, e[:, 0], e[:, 1], pic50_lower=-2.0)
+        assert abs(ss[k] - rs) <= 1e-6 * max(rs, 1.0)
+    assert best_fit_batch(2, [])[0].shape == (0, 3)
