@@ -140,11 +140,15 @@ def hierarchical_start(experiments, locs, best_fits=None):
     if sigma_cur <= locs[3]:
         sigma_cur = locs[3] + 0.1
 
+    hills = np.maximum(best_fits[:, 1], 1e-12)
+
     def neg_loglik(x):
         if x[0] <= 0 or x[1] <= 0:
             return np.inf
         with np.errstate(all="ignore"):
-            return -np.sum(st.fisk.logpdf(np.maximum(best_fits[:, 1], 1e-12), c=x[1], scale=x[0], loc=0))
+            # -sum of st.fisk.logpdf(hills, c=x[1], scale=x[0]) written out (the generic scipy call costs 100 us)
+            z = hills / x[0]
+            return -np.sum(np.log(x[1] / x[0]) + (x[1] - 1.0) * np.log(z) - 2.0 * np.log1p(z ** x[1]))
     res = minimize(neg_loglik, [0.5, 0.5], method="Nelder-Mead")
     alpha_cur, beta_cur = res.x
     if not np.isfinite(alpha_cur) or alpha_cur <= locs[0]:
