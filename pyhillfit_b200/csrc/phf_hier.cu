@@ -372,6 +372,18 @@ static int launch_am_hier(const phf_am_config &cfg, int64_t n, double *state, co
     return check_launch("am_hier_kernel");
 }
 
+// phf_hier_thread.cu: one thread per chain, n_expts <= kHierThreadMaxExpts
+constexpr int kHierThreadMaxExpts = 6;
+// cfg.lanes_per_chain == 0 picks the thread kernel for at most 3 experiments (its Cholesky factor fits in registers and
+// 9-11 warps share an SM) once the launch has 80 chains per SM: measured on B200 (scripts/hier_probe.py, Ne = 3,
+// ms per 1000 iterations, lane kernel vs thread kernel): 9 856 chains 11.3 vs 11.4, 19 712: 20.0 vs 14.4,
+// 39 424: 38.8 vs 19.2; with 4 experiments the two kernels tie at 10 496 chains (12.6 vs 12.4).
+constexpr int kHierThreadAutoMaxExpts = 3;
+constexpr int kHierThreadMinChainsPerSm = 80;
+int am_hier_thread_launch(const phf_am_config &cfg, int32_t n_expts, int64_t n, double *state, const int32_t *dataset_id,
+                          const phf_hier_dataset *datasets, const phf_hier_point *points, const phf_hier_priors &pr,
+                          double *samples, cudaStream_t s);
+
 // phf_hier_big.cu
 int hier_big_target_launch(int64_t n, const double *theta, int32_t theta_stride, const double *cov0,
                            const int32_t *dataset_id, const phf_hier_dataset *datasets, const phf_hier_point *points,
@@ -447,6 +459,18 @@ extern "C" int phf_am_hier_run(const phf_am_config *cfg, int32_t n_expts, int64_
     cudaStream_t s = (cudaStream_t)stream;
     if (n_expts > PHF_HIER_MAX_EXPTS)
         return am_hier_big_launch(*cfg, n_expts, n_chains, state, dataset_id, datasets, points, *priors, samples, s);
+    // cfg.lanes_per_chain: 1 = one thread per chain (throughput form, n_expts <= 6), 16 / 32 = one lane per
+    // parameter row (latency form), 0 = chosen from the chain count (see kHierThreadMinChainsPerSm)
+    if (cfg->lanes_per_chain != 0 && cfg->lanes_per_chain != 1 && cfg->lanes_per_chain != 16 && cfg->lanes_per_chain != 32)
+        return set_error(PHF_EINVAL, "phf_am_hier_run: cfg.lanes_per_chain must be 0 (auto), 1, 16 or 32");
+    const bool thread_form = cfg->lanes_per_chain == 1 ||
+                             (cfg->lanes_per_chain == 0 && n_expts <= kHierThreadAutoMaxExpts &&
+                              n_chains >= (int64_t)sm_count() * kHierThreadMinChainsPerSm);
+    if (thread_form) {
+        if (n_expts > kHierThreadMaxExpts)
+            return set_error(PHF_ENOTSUP, "phf_am_hier_run: one thread per chain needs n_expts <= 6");
+        return am_hier_thread_launch(*cfg, n_expts, n_chains, state, dataset_id, datasets, points, *priors, samples, s);
+    }
 #define PHF_HIER_CASE(NE, G) \
     case NE: return launch_am_hier<G, 5 + 2 * NE>(*cfg, n_chains, state, dataset_id, datasets, points, *priors, samples, s)
     switch (n_expts) {

@@ -200,8 +200,13 @@ class HierarchicalSampler(_Base):
     """n independent chains of the hierarchical model; every chain's dataset has `n_expts` experiments."""
 
     def __init__(self, pack, dataset_id, theta0, priors, cov0=None, adapt_when=None, seed=1, chain_id_base=0,
-                 thinning=5, device=None):
+                 thinning=5, device=None, lanes=0):
+        """lanes: 1 = one thread per chain (throughput form, at most 6 experiments), 16 / 32 = one lane per parameter
+        row (latency form), 0 = the library picks from the chain count."""
         assert isinstance(pack, HierPack)
+        if lanes not in (0, 1, 16, 32):
+            raise ValueError("lanes must be 0, 1, 16 or 32")
+        self.lanes = int(lanes)
         theta0 = np.atleast_2d(np.asarray(theta0, dtype=np.float64))
         n, dim = theta0.shape
         ids = np.ascontiguousarray(dataset_id, dtype=np.int32).reshape(-1)

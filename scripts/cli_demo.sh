@@ -12,7 +12,7 @@ with open("data/crumb_data.csv", "w") as out:
         out.write("%s,%s,%d,%r,%r\n" % (row[0], row[1], row[2], float(row[3]), float(row[4])))
 PY
 export PYTHONPATH=$ROOT
-echo "== PyHillFit -a -m 2 (210 pairs, 500000 iterations each)"; S=$SECONDS; python -m pyhillfit_b200.PyHillFit --data-file data/crumb_data.csv -m 2 -a > run.log 2>&1; grep -E "chains x|wall" run.log; tail -2 run.log | grep -i -E "error|Traceback"; echo "wall $((SECONDS-S)) s"
+echo "== PyHillFit -a -m 2 (210 pairs, 500000 iterations each)"; S=$SECONDS; python -m pyhillfit_b200.PyHillFit --data-file data/crumb_data.csv -m 2 -a > run.log 2>&1; grep -E "chains x|wall| s$" run.log; tail -2 run.log | grep -i -E "error|Traceback"; echo "wall $((SECONDS-S)) s"
 du -sh output | tail -1; ls output/crumb_data/single-level | wc -l
 echo "== PyHillFit -a --hierarchical (210 pairs)"; S=$SECONDS; python -m pyhillfit_b200.PyHillFit --data-file data/crumb_data.csv -m 2 -a --hierarchical > run.log 2>&1; grep -E "hierarchical chains|wall" run.log; tail -2 run.log | grep -i -E "error|Traceback"; echo "wall $((SECONDS-S)) s"
 echo "== PyHillTemp (41 temperatures) x 2 models + compute_bayes_factors, drug 0 channel 0"
