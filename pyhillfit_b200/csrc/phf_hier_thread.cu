@@ -11,8 +11,10 @@
 //     warp's access to one element is 32 consecutive doubles, no bank conflicts); one warp per CTA, so nothing but
 //     __syncwarp is ever needed.  The Cholesky factor is dead once the proposal is formed: up to dim 11 (Ne <= 3,
 //     154 of the 210 Crumb pairs) it lives in registers for that phase, which leaves 20 KB of shared memory per warp
-//     and lets 9 warps share an SM (the kernel is latency-bound: a lone warp's iteration is a ~20 000-cycle serial
-//     chain, so resident warps are what buys throughput); larger dimensions keep it in shared memory;
+//     and lets 9-11 warps share an SM (the kernel is latency-bound: a lone warp's iteration is a ~20 000-cycle serial
+//     chain, so resident warps are what buys throughput); larger dimensions keep it in shared memory.  The warps of
+//     a CTA never synchronise (barriers that kept them in phase, to share the 60 KB loop body's instruction fetch,
+//     cost 6 %: datasets have 6-20 points, and warps with few points waited for the others);
 //   * the factor is built row by row (Cholesky-Banachiewicz): row i only needs the finished rows j < i from shared
 //     memory, and the proposal component theta*_i = theta_i + e^{loga/2} (L z)_i is formed from row i while it is
 //     still in registers;
@@ -85,7 +87,7 @@ PHF_DI double hier_thread_log_target(const double *T, const double (&th)[5 + 2 *
     // PU points at a time, predicated instead of looped: the PU evaluations are independent straight-line code in
     // one basic block, so ptxas interleaves them (a lone warp is otherwise a serial chain of 8-cycle DFMAs)
 #ifndef PHF_HIER_PU
-#define PHF_HIER_PU 1  // (measured: the rolled one-point loop beats 2-4 unrolled points -- smaller code, see the instruction-fetch note)
+#define PHF_HIER_PU 1  // (measured: the rolled one-point loop beats 2-4 unrolled points: 22.7 vs 25.1 ms, smaller code)
 #endif
     constexpr int PU = PHF_HIER_PU;
     for (int base = 0; base < npts; base += PU) {
@@ -183,12 +185,6 @@ __global__ void __launch_bounds__(32 * HierThreadCfg<NE>::kMaxWarps) __maxnreg__
 
     for (uint32_t it = 0; it < cfg.n_iters; ++it) {
         ++t;
-        // The loop body is ~60 KB of code, twice the 32 KB instruction cache of an SM, and a warp needs ~96 KB of
-        // instruction fetch per iteration: warps that drift apart each stream their own copy from L2 and the SM's
-        // fetch bandwidth, not its issue slots, bounds the kernel.  The CTA's warps therefore meet at a barrier three
-        // times per iteration (every warp runs the same iteration count, so the barriers are safe): in phase, one
-        // fetched line serves all of them.
-        __syncthreads();
         if ((it & 31u) == 0u) {  // gamma_s is a function of t only: lane L computes it for iteration t + L
             const uint32_t tl = t + (uint32_t)lane;
             const double g = tl > cfg.adapt_when  // PyHillFit.py:496-497
@@ -257,9 +253,7 @@ __global__ void __launch_bounds__(32 * HierThreadCfg<NE>::kMaxWarps) __maxnreg__
         }
 
         // ---- target, accept (PyHillFit.py:486-493) ----
-        __syncthreads();
         const double lt_star = hier_thread_log_target<NE>(T, star, pts, npts, pr);
-        __syncthreads();
         const bool accepted = log_u < lt_star - lt;
         if (accepted) {
 #pragma unroll
@@ -323,11 +317,21 @@ static int launch_am_hier_thread(const phf_am_config &cfg, int64_t n, double *st
     // share the instruction stream), fewer for smaller launches so that the chains still spread over all SMs
     int warps = cfg.block_threads > 0 ? cfg.block_threads / 32 : (int)((n + 32 * (int64_t)sm_count() - 1) / (32 * (int64_t)sm_count()));
     warps = warps < 1 ? 1 : (warps > Cfg::kMaxWarps ? Cfg::kMaxWarps : warps);
-    const size_t smem = Cfg::kWarpDoubles * sizeof(double) * (size_t)warps;
     auto kern = am_hier_thread_kernel<NE>;
     cudaError_t e;
-    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)))
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(Cfg::kWarpDoubles * sizeof(double) * (size_t)Cfg::kMaxWarps))))
         return set_cuda_error(e, "cudaFuncSetAttribute");
+    // the register file is handed out in allocation units that differ between devices: ask the runtime whether a CTA of
+    // this size is resident at all and fall back to smaller CTAs otherwise
+    for (; warps > 1; --warps) {
+        int resident = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, 32 * warps,
+                                                          Cfg::kWarpDoubles * sizeof(double) * (size_t)warps);
+        if (e) return set_cuda_error(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+        if (resident >= 1) break;
+    }
+    const size_t smem = Cfg::kWarpDoubles * sizeof(double) * (size_t)warps;
     const int64_t per_cta = 32 * (int64_t)warps;
     const unsigned grid = (unsigned)((n + per_cta - 1) / per_cta);
     kern<<<grid, 32 * warps, smem, s>>>(cfg, n, state, dataset_id, datasets, points, pr, samples);
