@@ -128,6 +128,10 @@ int phf_am_single_init(int model, int64_t n_chains, const double *theta0 /* [n,d
  * pass the total over all launches that run concurrently */
 int phf_am_single_lanes(int64_t n_chains);
 
+/* resident CTAs per SM of the sampler kernel for (model, lanes per chain) at a CTA size and dynamic shared-memory
+ * size on the current device (the runtime's occupancy calculator; a tuning query, < 0 on error) */
+int phf_am_single_resident_ctas(int model, int lanes, int block_threads, int64_t smem_bytes);
+
 /*
  * Run cfg->n_iters iterations of every chain.  `samples` ([n_chains, rows_capacity, d+1], or
  * [rows_capacity, n_chains, d+1] with cfg->sample_layout = PHF_SAMPLES_ROW_MAJOR; may be NULL)

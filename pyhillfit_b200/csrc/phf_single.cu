@@ -488,3 +488,23 @@ extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, dou
 #undef PHF_AM_CASE
     return set_error(PHF_EINVAL, "no kernel variant for this (model, lanes, occupancy hint)");
 }
+
+// Resident CTAs per SM of the sampler kernel variant (model, lanes, default register budget) for a CTA size: what the
+// runtime's occupancy calculator says for the current device (a tuning / diagnostic query; returns < 0 on error).
+extern "C" int phf_am_single_resident_ctas(int model, int lanes, int block_threads, int64_t smem_bytes)
+{
+    int n = 0;
+    cudaError_t e = cudaErrorInvalidValue;
+#define PHF_OCC_CASE(M, G)                                                                                           \
+    if (model == M && lanes == G)                                                                                    \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, am_single_kernel<M, G, 3>, block_threads, (size_t)smem_bytes)
+    PHF_OCC_CASE(1, 1);
+    PHF_OCC_CASE(1, 2);
+    PHF_OCC_CASE(1, 4);
+    PHF_OCC_CASE(2, 1);
+    PHF_OCC_CASE(2, 2);
+    PHF_OCC_CASE(2, 4);
+#undef PHF_OCC_CASE
+    if (e) return set_cuda_error(e, "phf_am_single_resident_ctas");
+    return n;
+}

@@ -14,5 +14,7 @@ ncu --set full --clock-control none --import-source on -k regex:am_single_kernel
 ncu --set full --clock-control none --import-source on -k regex:am_single_kernel -s 2 -c 1 -o $O/${TAG}_g1 -f \
     python scripts/prof_run.py 1024 500 2 1 > $O/${TAG}_ncu_g1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:am_hier_kernel -s 2 -c 1 -o $O/${TAG}_hier3 -f \
-    python scripts/prof_hier.py > $O/${TAG}_ncu_hier.log 2>&1
+    python scripts/prof_hier.py 3 256 500 16 > $O/${TAG}_ncu_hier.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:am_hier_thread_kernel -s 2 -c 1 -o $O/${TAG}_hier_thread -f \
+    python scripts/prof_hier.py 3 256 500 1 > $O/${TAG}_ncu_hier_thread.log 2>&1
 ls -la $O/${TAG}_*
