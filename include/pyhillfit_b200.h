@@ -101,9 +101,11 @@ typedef struct phf_am_config {
     uint64_t chain_id_base;      /* global id of local chain 0 (ranks shard one global chain list) */
     int32_t stage_groups;        /* shared-memory staging capacity per CTA in dose groups / points (0: read via L1) */
     int32_t block_threads;       /* 0: library default (threads per CTA, multiple of 32, <= 128) */
-    int32_t lanes_per_chain;     /* single-level only: 1, 2 or 4 lanes cooperate on one chain; 0: chosen from
-                                    n_chains (phf_am_single_lanes).  Results of different lane counts agree to
-                                    rounding (the reduction order differs), not bit for bit. */
+    int32_t lanes_per_chain;     /* single-level: 1, 2 or 4 lanes cooperate on one chain; 0: chosen from n_chains
+                                    (phf_am_single_lanes).  Hierarchical: 16 / 32 = one lane per parameter row, 1 = one
+                                    thread per chain (n_expts <= 6), 0: chosen from n_expts and n_chains.  Results of
+                                    different lane counts agree to rounding (the reduction order differs), not bit
+                                    for bit. */
     int32_t min_ctas_hint;       /* single-level only, 0: library default (3).  Register budget of the kernel variant,
                                     as the minimum number of 128-thread CTAs per SM it is compiled for: 2 -> 255
                                     registers, 3 -> 168, 4 -> 128, 6 -> 80.  A tuning knob; results do not depend on it. */
