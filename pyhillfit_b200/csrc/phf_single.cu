@@ -417,13 +417,16 @@ extern "C" int phf_am_single_init(int model, int64_t n_chains, const double *the
 
 extern "C" int phf_am_single_lanes(int64_t n_chains)
 {
-    // Lanes are added while every lane of every chain can be resident at once at the kernels' register budget
-    // (168 registers -> 384 threads per SM): measured on B200, a launch that does not fit in one wave, or that fits
-    // only with a tighter register cap (spills), is slower than the same launch with fewer lanes.  `n_chains`
-    // should count the chains of ALL launches that run concurrently (e.g. models 1 and 2 on two streams).
-    const int64_t resident = (int64_t)sm_count() * 384;
-    if (n_chains * 4 <= resident) return 4;
-    if (n_chains * 2 <= resident) return 2;
+    // Two lanes per chain while every lane of every chain is resident at once at the kernels' register budget (168
+    // registers -> 384 threads per SM): measured on B200, a launch that does not fit in one wave, or that fits only
+    // with a tighter register cap (spills), is slower than the same launch with fewer lanes.  Four lanes only shorten
+    // the iteration of a lone warp from 2191 to 2020 cycles (model 2; scripts/occupancy_probe.py) and double the
+    // redundant work, so they pay only while a sub-partition holds a single warp (4 736 chains on 148 SMs: 4.49e9
+    // against 4.18e9 chain-it/s; at 9 472 chains two lanes give 8.3e9 against 7.7e9).  `n_chains` should count the
+    // chains of ALL launches that run concurrently (e.g. models 1 and 2 on two streams).
+    const int64_t sms = sm_count();
+    if (n_chains * 4 <= sms * 128) return 4;
+    if (n_chains * 2 <= sms * 384) return 2;
     return 1;
 }
 

@@ -46,7 +46,7 @@ def test_config2_all_pairs_64_chains(table, crumb_pack, model):
     theta0 = theta0 if model == 2 else theta0[:, [0, 2]]
     kw = dict(variant="fit", adapt_when=200, seed=25, thinning=5, burn_rows=0)
     a = SingleLevelSampler(model, crumb_pack, ids, 1.0, theta0, **kw)
-    assert a.lanes == 4                       # 13 440 x 4 lanes fit in one wave at 168 registers
+    assert a.lanes == 2                       # more than one warp per sub-partition: two lanes (phf_am_single_lanes)
     whole = a.run(1000).cpu().numpy()
     assert whole.shape == (13440, 200, d + 1)
     _rows_match_target(model, crumb_pack, ids, np.ones(len(ids)), whole[:, ::20, :])
