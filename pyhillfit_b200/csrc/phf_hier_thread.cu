@@ -129,20 +129,20 @@ template <int NE>
 struct HierThreadCfg {
     static constexpr int DIM = 5 + 2 * NE, NT = DIM * (DIM + 1) / 2;
     static constexpr bool kFactorInRegs = NE <= 3;
-    // registers are allocated to a CTA in units of four warps: 12 warps x 32 threads x 168 registers fill an SM's
-    // register file (BASELINE config 3 needs 8.3 warps per SM for its 39 424 three-experiment chains in ONE wave;
-    // at more than 170 registers an SM holds 8 warps and the launch takes two)
+    // BASELINE config 3 needs 8.3 warps per SM for its 39 424 three-experiment chains in ONE wave.  Measured on B200:
+    // a 9-warp CTA is resident at 168 registers per thread and not at 192, 200 or 224 (the launch fails, or the
+    // occupancy query below sends it to 8 warps and a second wave: 23.2 instead of 18.1 ms per 1000 iterations),
+    // although 9 x 32 x 224 is below the 65 536 registers of an SM -- the file is handed out in coarser units.
     static constexpr int kMaxRegs = kFactorInRegs ? 168 : 255;
     static constexpr size_t kWarpDoubles = (size_t)((kFactorInRegs ? NT : 2 * NT) + DIM) * 32 + 32;  // shared memory per warp
     static constexpr int kMaxWarps = kFactorInRegs ? 11 : (int)((220 * 1024) / (kWarpDoubles * 8));  // per SM (shared memory)
 };
 
 template <int NE>
-__global__ void __launch_bounds__(32 * HierThreadCfg<NE>::kMaxWarps) __maxnreg__(HierThreadCfg<NE>::kMaxRegs) am_hier_thread_kernel(phf_am_config cfg, int64_t n, double *__restrict__ state,
-                                                            const int32_t *__restrict__ dataset_id,
-                                                            const phf_hier_dataset *__restrict__ datasets,
-                                                            const phf_hier_point *__restrict__ points,
-                                                            phf_hier_priors pr, double *__restrict__ samples)
+__global__ void __launch_bounds__(32 * HierThreadCfg<NE>::kMaxWarps) __maxnreg__(HierThreadCfg<NE>::kMaxRegs)
+    am_hier_thread_kernel(phf_am_config cfg, int64_t n, double *__restrict__ state,
+                          const int32_t *__restrict__ dataset_id, const phf_hier_dataset *__restrict__ datasets,
+                          const phf_hier_point *__restrict__ points, phf_hier_priors pr, double *__restrict__ samples)
 {
     constexpr int DIM = 5 + 2 * NE, NT = DIM * (DIM + 1) / 2, NF = PHF_STATE_SIZE(DIM);
     constexpr int NPAIR = (DIM + 1) / 2;  // normal pairs per iteration: pair q feeds parameters 2q, 2q+1
