@@ -17,9 +17,10 @@ def table():
     return Table("crumb_data")
 
 
-@pytest.mark.parametrize("drug,channel", [("Amiodarone", "hERG"), ("Dofetilide", "hERG")])
-def test_hierarchical_posterior_matches_reference_chain(table, drug, channel):
-    """64 GPU chains vs one reference chain (python/PyHillFit.py:481-511 loop + :173-193 target, numpy RNG, 2e5
+@pytest.mark.parametrize("drug,channel,lanes", [("Amiodarone", "hERG", 0), ("Dofetilide", "hERG", 0),
+                                                ("Amiodarone", "hERG", 1)])
+def test_hierarchical_posterior_matches_reference_chain(table, drug, channel, lanes):
+    """(lanes = 0: the lane-per-parameter kernel; 1: the thread-per-chain kernel.)  64 GPU chains vs one reference chain (python/PyHillFit.py:481-511 loop + :173-193 target, numpy RNG, 2e5
     iterations): 5/25/50/75/95 % quantiles of all 5+2Ne parameters within 5 standard errors of the reference chain's quantile estimates."""
     from pyhillfit_b200.packing import HierPack
     from pyhillfit_b200.sampler import HierarchicalSampler, hier_priors
@@ -31,7 +32,8 @@ def test_hierarchical_posterior_matches_reference_chain(table, drug, channel):
     # same length and burn-in as the reference run: adaptive-Metropolis tails fill in slowly (at 6e4 iterations both
     # this sampler and the CPU oracle give a 6 % narrower 95 % point for sigma than at 2e5)
     nch, iters, thin = 64, int(g[key + "_iters"]), 5
-    s = HierarchicalSampler(pack, np.zeros(nch, dtype=np.int32), np.tile(theta0, (nch, 1)), pr, seed=99, thinning=thin)
+    s = HierarchicalSampler(pack, np.zeros(nch, dtype=np.int32), np.tile(theta0, (nch, 1)), pr, seed=99, thinning=thin,
+                            lanes=lanes)
     smp = s.run(iters).cpu().numpy()
     burn = (iters // thin + 1) // 4
     d = len(theta0)
