@@ -569,8 +569,50 @@ def other_configs(torch, dev, pack):
             done.record(st)
             torch.cuda.current_stream().wait_event(done)
     tot_t = _timed(torch, all_at_once)
+    # the same through phf_am_hier_run_host: pinned host buffers in and out, row-major samples, one host thread per Ne
+    import ctypes as C
+    from pyhillfit_b200 import _lib
+    L = _lib.load()
+    jobs = []
+    for hs, _, _ in hier:
+        st = torch.empty((hs.n, _lib.state_size(hs.d)), dtype=torch.float64).pin_memory()
+        st.copy_(hs.state.cpu())
+        smp = torch.empty((K3 // 5, hs.n, hs.d + 1), dtype=torch.float64).pin_memory()
+        jobs.append(dict(hs=hs, state=st, samples=smp, ids=np.ascontiguousarray(hs.dataset_id.cpu().numpy()), t0=hs.t))
+
+    def host_call(j):
+        hs = j["hs"]
+        cfg = _lib.AmConfig(model=0, reset_mean_at_adapt=0, t0=j["t0"], n_iters=K3, thinning=5, adapt_when=hs.adapt_when,
+                            burn_rows=0xFFFFFFFF, rows_capacity=K3 // 5, seed=hs.seed, chain_id_base=0, stage_groups=0,
+                            block_threads=0, lanes_per_chain=0, sample_layout=_lib.SAMPLES_ROW_MAJOR)
+        _lib.check(L.phf_am_hier_run_host(C.byref(cfg), hs.n_expts, hs.n, j["state"].data_ptr(), j["ids"].ctypes.data,
+                                          hs.pack.n_datasets, hs.pack.datasets.ctypes.data, len(hs.pack.points),
+                                          hs.pack.points.ctypes.data, C.byref(pr), j["samples"].data_ptr(), 8,
+                                          dev.index), "phf_am_hier_run_host")
+        j["t0"] += K3
+
+    def host_step():
+        th = [threading.Thread(target=host_call, args=(j,)) for j in jobs]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+    host_step()
+    torch.cuda.synchronize(dev)
+    e2e_t = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        host_step()
+        e2e_t.append(time.perf_counter() - t0)
+    e2e3 = {"value": tot_n * K3 / min(e2e_t), "unit": UNIT,
+            "h2d_bytes_per_step": int(sum(j["state"].numel() * 8 + j["ids"].nbytes + j["hs"].pack.points.nbytes +
+                                          j["hs"].pack.datasets.nbytes for j in jobs)),
+            "d2h_bytes_per_step": int(sum((j["samples"].numel() + j["state"].numel()) * 8 for j in jobs)),
+            "api": "phf_am_hier_run_host (pinned host buffers, row-major samples, 8 overlapped segments/call, one host "
+                   "thread per number of experiments), best of 3"}
+    del jobs
     out["config3_hierarchical"] = {"chains": tot_n, "iters": K3, "value": tot_n * K3 / tot_t, "unit": UNIT,
-                                   "value_back_to_back": tot_n * K3 / serial_t,
+                                   "value_back_to_back": tot_n * K3 / serial_t, "e2e": e2e3,
                                    "note": "dim 11..17, four launches (Ne = 3, 4, 5, 6) on four streams; Ne = 3 (39 424 "
                                            "chains) runs one thread per chain, the others one lane per parameter"}
     return out

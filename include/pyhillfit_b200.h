@@ -109,7 +109,7 @@ typedef struct phf_am_config {
     int32_t min_ctas_hint;       /* single-level only, 0: library default (3).  Register budget of the kernel variant,
                                     as the minimum number of 128-thread CTAs per SM it is compiled for: 2 -> 255
                                     registers, 3 -> 168, 4 -> 128, 6 -> 80.  A tuning knob; results do not depend on it. */
-    int32_t sample_layout;       /* single-level only.  PHF_SAMPLES_CHAIN_MAJOR (0): samples[chain][row][d+1], one chain's
+    int32_t sample_layout;       /* PHF_SAMPLES_CHAIN_MAJOR (0): samples[chain][row][d+1], one chain's
                                     rows contiguous (what np.savetxt of one chain wants).  PHF_SAMPLES_ROW_MAJOR (1):
                                     samples[row][chain][d+1], one saved iteration of ALL chains contiguous: a warp's
                                     write-out is one coalesced run and a block of rows is one contiguous region on the
@@ -188,7 +188,9 @@ int phf_am_hier_init(int32_t n_expts, int64_t n_chains, const double *theta0 /* 
 
 int phf_am_hier_run(const phf_am_config *cfg, int32_t n_expts, int64_t n_chains, double *state,
                     const int32_t *dataset_id, const phf_hier_dataset *datasets, const phf_hier_point *points,
-                    const phf_hier_priors *priors /* HOST */, double *samples /* [n, rows_capacity, dim+1] */,
+                    const phf_hier_priors *priors /* HOST */,
+                    double *samples /* [n, rows_capacity, dim+1], or [rows_capacity, n, dim+1] with
+                                       cfg->sample_layout = PHF_SAMPLES_ROW_MAJOR; may be NULL */,
                     void *stream);
 
 /*
@@ -213,6 +215,13 @@ int phf_am_single_run_host(const phf_am_config *cfg, int64_t n_chains, double *s
                            const double *temperature, int32_t n_datasets, const phf_dataset *datasets,
                            int32_t n_groups, const phf_dose_group *groups, double *samples, int32_t n_segments,
                            int32_t device);
+
+/* The same for the hierarchical sampler (python/PyHillFit.py:431-511 with numpy arrays in and out): all chains of
+ * a call share n_expts; `priors` is a HOST pointer as everywhere. */
+int phf_am_hier_run_host(const phf_am_config *cfg, int32_t n_expts, int64_t n_chains, double *state,
+                         const int32_t *dataset_id, int32_t n_datasets, const phf_hier_dataset *datasets,
+                         int32_t n_points, const phf_hier_point *points, const phf_hier_priors *priors,
+                         double *samples, int32_t n_segments, int32_t device);
 
 /* ------------------------------------------------------------------------------------------------
  * Chain / sample files.  Replaces np.savetxt at python/PyHillFit.py:514-515, 524-525, 866-867 and

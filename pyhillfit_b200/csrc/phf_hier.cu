@@ -261,7 +261,10 @@ __global__ void __launch_bounds__(128, hier_min_ctas(DIM)) am_hier_kernel(phf_am
     uint32_t until_save = cfg.thinning - (t % cfg.thinning);
     uint32_t row = t / cfg.thinning;
     const uint32_t row_base = row + 1;
-    double *out = samples ? samples + (size_t)c * cfg.rows_capacity * (DIM + 1) : nullptr;
+    // chain-major: rows of a chain DIM+1 doubles apart; row-major: n chains apart (phf_am_config.sample_layout)
+    const bool row_major = cfg.sample_layout == PHF_SAMPLES_ROW_MAJOR;
+    double *out = samples ? samples + (row_major ? (size_t)c : (size_t)c * cfg.rows_capacity) * (DIM + 1) : nullptr;
+    const size_t row_stride = row_major ? (size_t)n * (DIM + 1) : (size_t)(DIM + 1);
     double gam_lane = 0.0;
 
     for (uint32_t it = 0; it < cfg.n_iters; ++it) {
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(128, hier_min_ctas(DIM)) am_hier_kernel(phf_am
             until_save = cfg.thinning;
             ++row;
             if (out && active) {
-                double *o = out + (size_t)(row - row_base) * (DIM + 1);
+                double *o = out + (size_t)(row - row_base) * row_stride;
                 if (row_ok) o[gl] = th_j;
                 if (gl == DIM) o[DIM] = lt;
             }
@@ -447,8 +450,8 @@ extern "C" int phf_am_hier_run(const phf_am_config *cfg, int32_t n_expts, int64_
     if (!cfg || !priors) return set_error(PHF_EINVAL, "phf_am_hier_run: cfg/priors is NULL");
     if (n_expts < 1 || n_expts > PHF_HIER_BIG_MAX_EXPTS) return set_error(PHF_ENOTSUP, "n_expts outside 1..128");
     if (cfg->thinning == 0) return set_error(PHF_EINVAL, "cfg.thinning must be >= 1");
-    if (cfg->sample_layout != PHF_SAMPLES_CHAIN_MAJOR)
-        return set_error(PHF_ENOTSUP, "phf_am_hier_run: samples are chain-major (cfg.sample_layout must be 0)");
+    if (cfg->sample_layout != PHF_SAMPLES_CHAIN_MAJOR && cfg->sample_layout != PHF_SAMPLES_ROW_MAJOR)
+        return set_error(PHF_EINVAL, "cfg.sample_layout must be PHF_SAMPLES_CHAIN_MAJOR or PHF_SAMPLES_ROW_MAJOR");
     if (n_chains < 0 || (n_chains > 0 && (!state || !dataset_id || !datasets || !points)))
         return set_error(PHF_EINVAL, "phf_am_hier_run: null pointer");
     if ((uint64_t)cfg->t0 + cfg->n_iters > 0xFFFFFFFFull) return set_error(PHF_EINVAL, "iteration counter overflow");

@@ -178,7 +178,9 @@ __global__ void __launch_bounds__(32) am_hier_big_kernel(phf_am_config cfg, int3
     uint32_t until_save = cfg.thinning - (t % cfg.thinning);
     uint32_t row = t / cfg.thinning;
     const uint32_t row_base = row + 1;
-    double *out = samples ? samples + (size_t)c * cfg.rows_capacity * (dim + 1) : nullptr;
+    const bool row_major = cfg.sample_layout == PHF_SAMPLES_ROW_MAJOR;  // phf_am_config.sample_layout
+    double *out = samples ? samples + (row_major ? (size_t)c : (size_t)c * cfg.rows_capacity) * (dim + 1) : nullptr;
+    const size_t row_stride = row_major ? (size_t)n * (dim + 1) : (size_t)(dim + 1);
     const int n_pairs = (dim + 1) / 2;
 
     for (uint32_t it = 0; it < cfg.n_iters; ++it) {
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(32) am_hier_big_kernel(phf_am_config cfg, int3
             until_save = cfg.thinning;
             ++row;
             if (out) {
-                double *o = out + (size_t)(row - row_base) * (dim + 1);
+                double *o = out + (size_t)(row - row_base) * row_stride;
                 for (int j = lane; j < dim; j += 32) o[j] = th[j];
                 if (lane == 0) o[dim] = lt;
             }

@@ -181,7 +181,10 @@ __global__ void __launch_bounds__(32 * HierThreadCfg<NE>::kMaxWarps) __maxnreg__
     uint32_t until_save = cfg.thinning - (t % cfg.thinning);
     uint32_t row = t / cfg.thinning;
     const uint32_t row_base = row + 1;
-    double *out = samples ? samples + (size_t)c * cfg.rows_capacity * (DIM + 1) : nullptr;
+    // chain-major: rows of a chain DIM+1 doubles apart; row-major: n chains apart (phf_am_config.sample_layout)
+    const bool row_major = cfg.sample_layout == PHF_SAMPLES_ROW_MAJOR;
+    double *out = samples ? samples + (row_major ? (size_t)c : (size_t)c * cfg.rows_capacity) * (DIM + 1) : nullptr;
+    const size_t row_stride = row_major ? (size_t)n * (DIM + 1) : (size_t)(DIM + 1);
 
     for (uint32_t it = 0; it < cfg.n_iters; ++it) {
         ++t;
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(32 * HierThreadCfg<NE>::kMaxWarps) __maxnreg__
             until_save = cfg.thinning;
             ++row;
             if (out && active) {
-                double *o = out + (size_t)(row - row_base) * (DIM + 1);
+                double *o = out + (size_t)(row - row_base) * row_stride;
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) o[k] = th[k];
                 o[DIM] = lt;

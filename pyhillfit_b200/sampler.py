@@ -238,20 +238,24 @@ class HierarchicalSampler(_Base):
     def initial_row(self):
         return self.state[:, :self.d + 1].clone()
 
-    def run(self, n_iters, samples=None):
+    def run(self, n_iters, samples=None, row_major=False):
+        """Advance every chain by n_iters; returns the rows saved by this call: [n, rows, dim+1], or [rows, n, dim+1]
+        with row_major=True (one saved iteration of all chains contiguous, as in SingleLevelSampler.run)."""
         torch = self.torch
         rows = self.rows_for(n_iters)
+        ax_n, ax_r = (1, 0) if row_major else (0, 1)
         if samples is None:
-            samples = torch.empty((self.n, max(rows, 1), self.d + 1), dtype=torch.float64, device=self.device)
-        assert samples.shape[0] == self.n and samples.shape[2] == self.d + 1 and samples.is_contiguous()
-        cfg = self._config(n_iters, samples.shape[1])
+            shape = (max(rows, 1), self.n, self.d + 1) if row_major else (self.n, max(rows, 1), self.d + 1)
+            samples = torch.empty(shape, dtype=torch.float64, device=self.device)
+        assert samples.shape[ax_n] == self.n and samples.shape[2] == self.d + 1 and samples.is_contiguous()
+        cfg = self._config(n_iters, samples.shape[ax_r], row_major)
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().phf_am_hier_run(C.byref(cfg), self.n_expts, self.n, self.state.data_ptr(),
                                                    self.dataset_id.data_ptr(), self.ds_dev.data_ptr(),
                                                    self.pts_dev.data_ptr(), C.byref(self.priors),
                                                    samples.data_ptr(), _lib.current_stream_ptr()), "phf_am_hier_run")
         self.t += int(n_iters)
-        return samples[:, :rows]
+        return samples[:rows] if row_major else samples[:, :rows]
 
 
 def hier_priors():

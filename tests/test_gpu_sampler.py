@@ -329,3 +329,87 @@ def test_hier_thread_kernel_is_resumable_and_matches_the_lane_kernel(table, ne):
     same = np.isclose(whole[:64], lane_rows, rtol=1e-9, atol=1e-9).all(axis=(1, 2))
     assert same.mean() >= 0.9, same.mean()    # (a rounding-level difference may flip an accept in a few chains)
     assert 0.05 < a.acceptance().mean() < 0.6
+
+
+def _hier_setup(table, ne, per, seed=3):
+    from pyhillfit_b200.packing import HierPack
+    pairs = [p for p in table.pairs() if len(table.experiments(*p)) == ne][:3]
+    pack = HierPack([table.experiments(*p) for p in pairs])
+    ids = np.repeat(np.arange(len(pairs), dtype=np.int32), per)[:-3]      # ragged last warp / group
+    rng = np.random.default_rng(seed + ne)
+    theta0 = np.concatenate([np.tile([1.0, 4.0, 6.0, 0.3], (len(ids), 1)),
+                             np.tile([5.0, 1.0], (len(ids), ne)) + rng.uniform(-0.3, 0.3, (len(ids), 2 * ne)),
+                             np.full((len(ids), 1), 8.0)], axis=1)
+    return pack, ids, theta0
+
+
+@pytest.mark.parametrize("ne,lanes", [(3, 1), (3, 16), (4, 1), (5, 16), (6, 32)])
+def test_hier_row_major_samples_are_the_transpose(table, ne, lanes):
+    """cfg.sample_layout = PHF_SAMPLES_ROW_MAJOR in the hierarchical kernels (thread per chain and lane per parameter):
+    the same rows, [row][chain][dim+1] instead of [chain][row][dim+1]; state identical; segmented run included."""
+    from pyhillfit_b200.sampler import HierarchicalSampler, hier_priors
+    pr = hier_priors()[0]
+    pack, ids, theta0 = _hier_setup(table, ne, 40)
+    kw = dict(adapt_when=40, seed=21, chain_id_base=9, thinning=5, lanes=lanes)
+    a = HierarchicalSampler(pack, ids, theta0, pr, **kw)
+    b = HierarchicalSampler(pack, ids, theta0, pr, **kw)
+    want = a.run(120).cpu().numpy()
+    got = np.concatenate([b.run(70, row_major=True).cpu().numpy(), b.run(50, row_major=True).cpu().numpy()], axis=0)
+    assert got.shape == (24, len(ids), 5 + 2 * ne + 1)
+    assert np.array_equal(got.transpose(1, 0, 2), want)
+    assert np.array_equal(a.state.cpu().numpy(), b.state.cpu().numpy())
+
+
+def test_hier_many_experiments_row_major():
+    """the warp-per-chain kernel (dim 105) with row-major samples"""
+    from pyhillfit_b200.packing import HierPack
+    from pyhillfit_b200.sampler import HierarchicalSampler, hier_priors
+    pr = hier_priors()[0]
+    syn = Table("synthetic_data")
+    ex = [syn.experiments(d, c) for d, c in syn.pairs() if len(syn.experiments(d, c)) == 50][0]
+    ne, nch = 50, 3
+    rng = np.random.default_rng(1)
+    theta0 = np.concatenate([np.tile([1.0, 4.0, 6.0, 0.3], (nch, 1)),
+                             np.tile([6.0, 1.0], (nch, ne)) + rng.uniform(-0.2, 0.2, (nch, 2 * ne)),
+                             np.full((nch, 1), 8.0)], axis=1)
+    kw = dict(adapt_when=40, seed=8, chain_id_base=77, thinning=5)
+    a = HierarchicalSampler(HierPack([ex]), np.zeros(nch, dtype=np.int32), theta0, pr, **kw)
+    b = HierarchicalSampler(HierPack([ex]), np.zeros(nch, dtype=np.int32), theta0, pr, **kw)
+    want = a.run(60).cpu().numpy()
+    got = b.run(60, row_major=True).cpu().numpy()
+    assert np.array_equal(got.transpose(1, 0, 2), want)
+
+
+@pytest.mark.parametrize("ne,lanes", [(3, 1), (4, 16)])
+def test_hier_host_buffer_entry_point(table, ne, lanes):
+    """phf_am_hier_run_host: numpy in, numpy out, identical to the device-pointer path, both sample layouts."""
+    import torch
+    from pyhillfit_b200 import _lib
+    from pyhillfit_b200.sampler import HierarchicalSampler, hier_priors
+    pr = hier_priors()[0]
+    pack, ids, theta0 = _hier_setup(table, ne, 30)
+    dim = 5 + 2 * ne
+    kw = dict(adapt_when=50, seed=13, chain_id_base=4, thinning=5, lanes=lanes)
+    ref = HierarchicalSampler(pack, ids, theta0, pr, **kw)
+    state0 = ref.state.cpu().numpy().copy()
+    want = ref.run(400).cpu().numpy()
+    rows, n = 80, len(ids)
+    L = _lib.load()
+    for layout, shape, nseg in ((_lib.SAMPLES_CHAIN_MAJOR, (n, rows, dim + 1), 3),
+                                (_lib.SAMPLES_ROW_MAJOR, (rows, n, dim + 1), 7)):
+        state = torch.from_numpy(state0.copy()).pin_memory().numpy()
+        samples = torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
+        cfg = _lib.AmConfig(model=0, reset_mean_at_adapt=0, t0=0, n_iters=400, thinning=5, adapt_when=50,
+                            burn_rows=0xFFFFFFFF, rows_capacity=rows, seed=13, chain_id_base=4, stage_groups=0,
+                            block_threads=0, lanes_per_chain=lanes, sample_layout=layout)
+        _lib.check(L.phf_am_hier_run_host(C.byref(cfg), ne, n, state.ctypes.data, ids.ctypes.data, pack.n_datasets,
+                                          pack.datasets.ctypes.data, len(pack.points), pack.points.ctypes.data,
+                                          C.byref(pr), samples.ctypes.data, nseg, 0), "phf_am_hier_run_host")
+        got = samples if layout == _lib.SAMPLES_CHAIN_MAJOR else samples.transpose(1, 0, 2)
+        assert np.array_equal(got, want)
+        assert np.array_equal(state, ref.state.cpu().numpy())
+    # argument errors come back as codes, not crashes
+    assert L.phf_am_hier_run_host(C.byref(cfg), 0, n, state.ctypes.data, ids.ctypes.data, pack.n_datasets,
+                                  pack.datasets.ctypes.data, len(pack.points), pack.points.ctypes.data, C.byref(pr),
+                                  samples.ctypes.data, 1, 0) != 0
+    assert b"n_expts" in L.phf_last_error()
