@@ -5,6 +5,8 @@ Every (pair, model, temperature, replicate) is one chain of the fused sampler; t
 temperature-1 log-likelihood of the saved post-burn rows in a register (no chain files, no second pass);
 ranks all-gather the per-chain means and the ladder is integrated with the reference's trapezium rule.
 """
+import time
+
 import numpy as np
 
 from . import dist as phf_dist
@@ -65,6 +67,7 @@ def run_ti(datasets, models=(1, 2), temps=None, replicates=1, iterations=500000,
                                                  co_resident_chains=(hi - lo) * (len(models) - 1))
             streams[model] = torch.cuda.Stream(device=dev)
         torch.cuda.synchronize(dev)
+        t_start = time.perf_counter()
         done = 0
         while done < iterations:
             k = min(segment, iterations - done)
@@ -75,6 +78,8 @@ def run_ti(datasets, models=(1, 2), temps=None, replicates=1, iterations=500000,
             if progress:
                 progress(done, iterations)
         torch.cuda.synchronize(dev)
+        out["sample_seconds"] = time.perf_counter() - t_start   # this rank's sampling phase (launch to synchronise)
+    t_gather = time.perf_counter()
     for model in models:
         d = 2 if model == 1 else 3
         nt = d * (d + 1) // 2
@@ -91,6 +96,7 @@ def run_ti(datasets, models=(1, 2), temps=None, replicates=1, iterations=500000,
         out["means_per_replicate_%d" % model] = means
         out["acceptance"][model] = acc
         out["log_py"][model] = log_py_from_means(temps, out["means"][model])
+    out["gather_seconds"] = time.perf_counter() - t_gather    # all-gathers + trapezium rule (first call: NCCL start-up)
     if 1 in out["log_py"] and 2 in out["log_py"]:
         out["B12"] = np.exp(out["log_py"][1] - out["log_py"][2])  # compute_bayes_factors.py:94
     return out

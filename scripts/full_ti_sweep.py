@@ -17,15 +17,22 @@ pd.init_process_group()
 table = Table("crumb_data")
 pairs = table.pairs()
 data = [table.concat(*p) for p in pairs]
+if ws > 1:     # bring the NCCL communicator up before the clock starts (its first collective takes about a second)
+    torch.distributed.all_reduce(torch.zeros(1, device="cuda"))
 torch.cuda.synchronize()
 t0 = time.time()
 out = ti.run_ti(data, replicates=reps, iterations=iters, thinning=5, burn_in_fraction=4, seed=1, segment=100000)
 torch.cuda.synchronize()
 dt = time.time() - t0
+ph = torch.tensor([out.get("sample_seconds", 0.0), out["gather_seconds"]], dtype=torch.float64, device="cuda")
+if ws > 1:
+    torch.distributed.all_reduce(ph, op=torch.distributed.ReduceOp.MAX)
 if rank == 0:
     n = len(pairs) * 2 * 41 * reps
     print("%d chains x %d iterations on %d GPU(s): %.2f s wall (%.3e chain-iterations/s incl. packing and launch overheads)"
           % (n, iters, ws, dt, n * iters / dt))
+    print("  sampling phase %.3f s (max over ranks, %.3e chain-iterations/s), all-gather + trapezium rule %.4f s"
+          % (float(ph[0]), n * iters / float(ph[0]), float(ph[1])))
     b = out["B12"]
     print("B12: min %.3g median %.3g max %.3g; pairs favouring model 2 (B12 < 1): %d of %d" % (b.min(), np.median(b), b.max(), int((b < 1).sum()), len(b)))
     for i in (0, 1, 2):
