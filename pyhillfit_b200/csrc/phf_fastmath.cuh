@@ -41,10 +41,49 @@ struct double2 {
 };
 #endif
 
+// exp / log: 1 = table-driven (a 3 KB lookup table staged in SHARED memory by PHF_STAGE_FASTMATH_TABLE: 128 (1/c, log c)
+// pairs and 64 double-double 2^(j/64); the polynomials shrink to degree 4 / 3, 11 fp64 instructions per call instead
+// of 22 / 18), 0 = the polynomial-only versions.  With the table T passed to every function is the shared-memory
+// table and the polynomial coefficients come straight from __constant__ memory.
+#ifndef PHF_FM_LUT
+#define PHF_FM_LUT 1
+#endif
+#if PHF_FM_LUT && PHF_FM_TABLE_MODE != 0
+#error "PHF_FM_LUT needs PHF_FM_TABLE_MODE == 0 (coefficients in __constant__ memory)"
+#endif
+#if defined(__CUDACC__)
+#define PHF_LUT_POLY static __constant__ __align__(16)
+#define PHF_LUT_TABLE static __device__ __align__(16) const
+#else
+#define PHF_LUT_POLY alignas(16) static const
+#define PHF_LUT_TABLE alignas(16) static const
+#endif
+
 namespace phf {
 namespace fm {
 
 #include "phf_fastmath_coeffs.inc"
+#include "phf_fastmath_lut.inc"
+
+// where a function finds the polynomial coefficients / the lookup table given the pointer its caller passes
+PHF_FM const double *coef(const double *T)
+{
+#if defined(__CUDA_ARCH__) && PHF_FM_LUT
+    (void)T;
+    return kFmTable;  // T is the shared-memory lookup table
+#else
+    return T;
+#endif
+}
+PHF_FM const double *lut(const double *T)
+{
+#if defined(__CUDA_ARCH__)
+    return T;
+#else
+    (void)T;
+    return kFmLut;  // host build: T is kFmTable
+#endif
+}
 
 // Every function below takes `T`, the base of the coefficient table: shared memory in the kernels (see
 // stage_table), kFmTable itself in the host build.
@@ -178,11 +217,37 @@ PHF_FM double sqrt_nonneg(double a)
 }
 
 // ---- exp(x); the argument is clamped to [-700, 700] (the callers' results saturate long before) -----
+#if PHF_FM_LUT
+// e^x = 2^(n >> 6) * 2^((n & 63)/64) * e^r, n = round(64 x / ln 2), |r| <= 0.0058: 11 fp64 instructions
+PHF_FM double exp_clamped(const double *T, double x)
+{
+    const double k64Log2eHi = 64.0 * 1.4426946640014648;         // 64 log2(e) to 21 bits (picks n only)
+    const double kLn2Hi64 = 0.693147182464599609375 / 64.0;      // n * kLn2Hi64 is exact (21 significant bits)
+    const double kLn2Lo64 = coef(T)[PHF_FM_KMISC + 0] * (1.0 / 64.0);
+    const double kMagic = 6755399441055744.0;                    // 1.5 * 2^52
+    {
+        const int hi = hi_word(x);
+        const bool big = (hi & 0x7fffffff) >= 0x4085e000;  // 0x4085e000'00000000 == 700.0; NaN too
+        x = make_double(big ? ((hi & 0x80000000) | 0x4085e000) : hi, big ? 0 : lo_word(x));
+    }
+    const double t = fma(x, k64Log2eHi, kMagic);
+    const int n = lo_word(t);
+    const double nf = t - kMagic;
+    double r = fma(nf, -kLn2Hi64, x);
+    r = fma(nf, -kLn2Lo64, r);
+    const double2 tj = *reinterpret_cast<const double2 *>(lut(T) + PHF_FM_LUT_EXP + 2 * (n & 63));  // 2^(j/64): hi, lo
+    const double r2 = r * r;
+    const double q = fma(fma(kFmExpQ[3], r, kFmExpQ[2]), r2, fma(kFmExpQ[1], r, kFmExpQ[0]));
+    const double p = fma(r2, q, r);                    // e^r - 1
+    const double v = fma(tj.x, p, tj.y) + tj.x;        // in [1, 2) up to rounding
+    return make_double(hi_word(v) + ((n >> 6) << 20), lo_word(v));  // * 2^(n >> 6), |n >> 6| <= 1010
+}
+#else
 PHF_FM double exp_clamped(const double *T, double x)
 {
     const double kLog2eHi = 1.4426946640014648;       // 0x3ff7154700000000: log2(e) to 21 bits (picks n only)
     const double kLn2Hi = 0.693147182464599609375;    // 0x3fe62e4300000000: n * kLn2Hi is exact
-    const double kLn2Lo = T[PHF_FM_KMISC + 0];         // ln 2 - kLn2Hi
+    const double kLn2Lo = coef(T)[PHF_FM_KMISC + 0];         // ln 2 - kLn2Hi
     const double kMagic = 6755399441055744.0;         // 1.5 * 2^52
     // clamp on the high word (5 integer instructions; fmin/fmax cost 12 on sm_100a): |x| >= 700 or NaN -> +-700
     {
@@ -200,17 +265,38 @@ PHF_FM double exp_clamped(const double *T, double x)
     xp[1] = r * r;
     xp[2] = xp[1] * xp[1];
     xp[3] = xp[2] * xp[2];
-    const double q = poly<0, 9>(T + PHF_FM_KEXPQ, xp);
+    const double q = poly<0, 9>(coef(T) + PHF_FM_KEXPQ, xp);
     const double p = fma(xp[1], q, r);                 // e^r - 1
     const double s = make_double((n + 1023) << 20, 0);  // 2^n, n in [-1010, 1010]
     return fma(s, p, s);
 }
+#endif
 
 // ---- log(x), x positive and normal --------------------------------------------------------------
+#if PHF_FM_LUT
+// x = 2^e m, m in [sqrt(1/2), sqrt 2); interval j of m (top 7 bits of its high-word offset) has (1/c_j, log c_j) in the
+// table: r = m / c_j - 1 by one FMA (|r| < 2^-8), log m = log c_j + r + r^2 P(r).  11 fp64 instructions, no MUFU.
 PHF_FM double log_pos(const double *T, double x)
 {
     const double kLn2Hi = 0.693147182464599609375;
-    const double kLn2Lo = T[PHF_FM_KMISC + 0];
+    const double kLn2Lo = coef(T)[PHF_FM_KMISC + 0];
+    const int k = hi_word(x) + (0x3ff00000 - 0x3fe6a09e);  // 0x3fe6a09e: high word of sqrt(1/2)
+    const int e = (k >> 20) - 1023;
+    const int off = k & 0x000fffff;
+    const double m = make_double(off + 0x3fe6a09e, lo_word(x));
+    const double2 cj = *reinterpret_cast<const double2 *>(lut(T) + 2 * (off >> (20 - PHF_FM_LUT_LOG_BITS)));
+    const double r = fma(m, cj.x, -1.0);
+    const double r2 = r * r;
+    const double pr = fma(r2 * r2, kFmLogP[4], fma(fma(kFmLogP[3], r, kFmLogP[2]), r2, fma(kFmLogP[1], r, kFmLogP[0])));
+    const double l1p = fma(r2, pr, r);  // log(1 + r)
+    const double ef = (double)e;
+    return fma(ef, kLn2Hi, cj.y) + fma(ef, kLn2Lo, l1p);
+}
+#else
+PHF_FM double log_pos(const double *T, double x)
+{
+    const double kLn2Hi = 0.693147182464599609375;
+    const double kLn2Lo = coef(T)[PHF_FM_KMISC + 0];
     // mantissa to [sqrt(1/2), sqrt(2)): 0x3fe6a09e is the high word of sqrt(1/2)
     const int k = hi_word(x) + (0x3ff00000 - 0x3fe6a09e);
     const int e = (k >> 20) - 1023;
@@ -227,12 +313,13 @@ PHF_FM double log_pos(const double *T, double x)
     xp[0] = f * f;
     xp[1] = xp[0] * xp[0];
     xp[2] = xp[1] * xp[1];
-    const double R = poly<0, 6>(T + PHF_FM_KLOGR, xp);
+    const double R = poly<0, 6>(coef(T) + PHF_FM_KLOGR, xp);
     const double ef = (double)e;
     // log x = e ln2 + 2 atanh(f) = e ln2_hi + (2f + (f^3 R + e ln2_lo))
     const double tail = fma(f * xp[0], R, ef * kLn2Lo);
     return fma(ef, kLn2Hi, fma(2.0, f, tail));
 }
+#endif
 
 // ---- erfcx(t) = exp(t^2) erfc(t), 0 <= t <= 1e140 --------------------------------------------------
 // erfcx(t) (1 + 2t) = P(q), q = (t - K)/(t + K): one polynomial on q in [-1, 1) covers the half line.
@@ -249,7 +336,7 @@ PHF_FM double erfcx_nonneg(const double *T, double t)
     xp[2] = xp[1] * xp[1];
     xp[3] = xp[2] * xp[2];
     xp[4] = xp[3] * xp[3];
-    const double P = poly<0, 22>(T + PHF_FM_KERFCXP, xp);
+    const double P = poly<0, 22>(coef(T) + PHF_FM_KERFCXP, xp);
     return P * (r * a);
 }
 
@@ -257,14 +344,14 @@ PHF_FM double erfcx_nonneg(const double *T, double t)
 //      on all of z <= 0 because the value never comes near zero there) -------------------------------
 PHF_FM double log_ndtr_nonpos(const double *T, double z)
 {
-    const double t = fabs(z) * T[PHF_FM_KMISC + 2];
+    const double t = fabs(z) * coef(T)[PHF_FM_KMISC + 2];
     return fma(-t, t, log_pos(T, 0.5 * erfcx_nonneg(T, t)));
 }
 
 // ---- sin and cos of 2 pi b / 2^32 ---------------------------------------------------------------
 PHF_FM void sincos_turn32(const double *T, uint32_t b, double &sn, double &cs)
 {
-    const double kScale = T[PHF_FM_KMISC + 1];  // pi / 2^31
+    const double kScale = coef(T)[PHF_FM_KMISC + 1];  // pi / 2^31
     const uint32_t bb = b + 0x20000000u;           // nearest multiple of a quarter turn
     const uint32_t quad = bb >> 30;
     const int32_t rem = (int32_t)(bb & 0x3fffffffu) - 0x20000000;  // [-2^29, 2^29)
@@ -273,8 +360,8 @@ PHF_FM void sincos_turn32(const double *T, uint32_t b, double &sn, double &cs)
     xp[0] = r * r;
     xp[1] = xp[0] * xp[0];
     xp[2] = xp[1] * xp[1];
-    const double S = poly<0, 5>(T + PHF_FM_KSINS, xp);
-    const double C = poly<0, 5>(T + PHF_FM_KCOSC, xp);
+    const double S = poly<0, 5>(coef(T) + PHF_FM_KSINS, xp);
+    const double C = poly<0, 5>(coef(T) + PHF_FM_KCOSC, xp);
     const double s0 = fma(r * xp[0], S, r);
     const double c0 = fma(xp[1], C, fma(-0.5, xp[0], 1.0));
     // rotate by quad quarter turns
@@ -288,7 +375,7 @@ PHF_FM void sincos_turn32(const double *T, uint32_t b, double &sn, double &cs)
 // ---- 10^x as exp(x ln 10) with a double-double ln 10 (model 1's 1/IC50) -----------------------------
 PHF_FM double exp10_clamped(const double *T, double x)
 {
-    const double kLn10Hi = T[PHF_FM_KMISC + 3], kLn10Lo = T[PHF_FM_KMISC + 4];
+    const double kLn10Hi = coef(T)[PHF_FM_KMISC + 3], kLn10Lo = coef(T)[PHF_FM_KMISC + 4];
     const double hi = x * kLn10Hi;
     const double lo = fma(x, kLn10Lo, fma(x, kLn10Hi, -hi));
     const double e = exp_clamped(T, hi);

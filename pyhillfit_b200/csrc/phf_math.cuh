@@ -15,6 +15,13 @@
     phf::fm::stage_table(T##_smem);                                   \
     __syncthreads();                                                  \
     const double *const T = T##_smem
+#elif PHF_FM_LUT
+// the exp / log lookup table (3 KB) goes to shared memory; T is what every fm:: function takes
+#define PHF_STAGE_FASTMATH_TABLE(T)                                                                     \
+    __shared__ __align__(16) double T##_lut[PHF_FM_LUT_SIZE];                                           \
+    for (int i_ = threadIdx.x; i_ < PHF_FM_LUT_SIZE; i_ += blockDim.x) T##_lut[i_] = phf::fm::kFmLut[i_]; \
+    __syncthreads();                                                                                    \
+    const double *const T = T##_lut
 #else
 #define PHF_STAGE_FASTMATH_TABLE(T) const double *const T = phf::fm::kFmTable
 #endif
