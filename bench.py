@@ -269,6 +269,7 @@ def main():
     ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per chain (0: library default)")
     ap.add_argument("--occupancy-hint", type=int, default=0, help="developer knob: min CTAs/SM variant")
+    ap.add_argument("--cta-order", type=int, default=0, help="developer knob: 0 chain blocks by decreasing cost, 1 index order")
     ap.add_argument("--serial-models", action="store_true", help="run the two models back to back on one stream")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -306,6 +307,7 @@ def main():
                                stage=not args.no_stage, block_threads=args.block_threads, lanes=args.lanes,
                                co_resident_chains=0 if args.serial_models else len(wl[3 - model]["ids"]))
         s.occupancy_hint = args.occupancy_hint
+        s.cta_order = args.cta_order
         samplers[model] = s
         buffers[model] = torch.empty((rows_per_step + 1, n, w["d"] + 1) if args.layout == "row" else
                                      (n, rows_per_step + 1, w["d"] + 1), dtype=torch.float64, device=dev)

@@ -115,7 +115,9 @@ typedef struct phf_am_config {
                                     write-out is one coalesced run and a block of rows is one contiguous region on the
                                     device and on the host (phf_am_single_run_host copies it back with plain
                                     contiguous transfers: 55 GB/s instead of 47 through the strided 2-D copy). */
-    int32_t reserved0;           /* must be 0 */
+    int32_t cta_order;           /* single-level only.  0: chain blocks are run in order of decreasing cost (censored
+                                    doses per dataset), which balances the SMs when the datasets differ; 1: in index
+                                    order.  Results do not depend on it. */
 } phf_am_config;
 #define PHF_SAMPLES_CHAIN_MAJOR 0
 #define PHF_SAMPLES_ROW_MAJOR 1

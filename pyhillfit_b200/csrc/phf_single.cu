@@ -201,11 +201,73 @@ PHF_DI void am_step(const double *T, const ChainConst &cc, ChainRegs<MODEL> &s, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA order.  Every chain of a launch runs the same number of iterations and (up to one wave) all CTAs are resident at
+// once, so the launch ends when its slowest sub-partition does -- and the cost of an iteration depends on the dataset:
+// each censored dose adds an erfcx + log evaluation (Crumb: 0 to 4 censored doses per pair, +40 % work for the
+// heaviest warps).  The block scheduler hands out CTAs in blockIdx order, round-robin over the SMs, so the launch
+// runs its chain blocks in order of DECREASING weight: every SM then gets a heavy, a middling and a light block
+// instead of whatever the caller's dataset order happens to put together.  Which CTA runs a chain block changes
+// nothing in the results.  Stateless: every CTA works out its own block in the prologue -- weight class of every
+// chain block (8 classes, from the block's first chain) into shared memory, counting sort by class, and the block
+// at sorted position blockIdx.x found by a ballot scan (index order within a class: deterministic).  A few
+// microseconds per launch, nothing allocated, no extra kernel; only for launches of sm_count < grid <= 4096 CTAs
+// (fewer: one CTA per SM, nothing to balance; more: several waves, which balance themselves).
+// ------------------------------------------------------------------------------------------------
+constexpr int kOrderClasses = 8;
+constexpr int kOrderMaxGrid = 4096;
+
+__device__ __forceinline__ int ordered_block_index(int cta_chains, const int32_t *__restrict__ dataset_id,
+                                                   const phf_dataset *__restrict__ datasets,
+                                                   const phf_dose_group *__restrict__ groups)
+{
+    __shared__ unsigned char cls[kOrderMaxGrid];
+    __shared__ int count[kOrderClasses], my_class, my_rank, chosen;
+    const int tid = threadIdx.x, n_ctas = gridDim.x;
+    if (tid < kOrderClasses) count[tid] = 0;
+    __syncthreads();
+    for (int b = tid; b < n_ctas; b += blockDim.x) {
+        const phf_dataset ds = datasets[dataset_id[(int64_t)b * cta_chains]];  // the block's first chain stands for it
+        int w = ds.n_groups > 4 ? ds.n_groups - 4 : 0;
+        for (int g = 0; g < ds.n_groups && g < 16; ++g) {
+            const phf_dose_group &Gd = groups[ds.group_begin + g];
+            w += (Gd.n0 > 0.0 ? 1 : 0) + (Gd.n100 > 0.0 ? 1 : 0);
+        }
+        w = w < kOrderClasses ? w : kOrderClasses - 1;
+        cls[b] = (unsigned char)w;
+        atomicAdd(&count[w], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int p = blockIdx.x, c = kOrderClasses - 1;
+        for (; c > 0 && p >= count[c]; --c) p -= count[c];  // heaviest class first
+        my_class = c;
+        my_rank = p;
+    }
+    __syncthreads();
+    if (tid < 32) {  // the my_rank-th block of class my_class, in index order
+        const int want = my_class, rank = my_rank;
+        int seen = 0;
+        for (int base = 0; base < n_ctas; base += 32) {
+            const int b = base + tid;
+            const unsigned m = __ballot_sync(0xffffffffu, b < n_ctas && cls[b] == want);
+            const int here = __popc(m);
+            if (seen + here > rank) {
+                if (tid == 0) chosen = base + (int)__fns(m, 0, rank - seen + 1);
+                break;  // (warp-uniform)
+            }
+            seen += here;
+        }
+    }
+    __syncthreads();
+    return chosen;
+}
+
 template <int MODEL, int G, int MINB>
 __global__ void __launch_bounds__(128, MINB)
     am_single_kernel(phf_am_config cfg, int64_t n, double *__restrict__ state, const int32_t *__restrict__ dataset_id,
                      const double *__restrict__ temperature, const phf_dataset *__restrict__ datasets,
-                     const phf_dose_group *__restrict__ groups, double *__restrict__ samples)
+                     const phf_dose_group *__restrict__ groups, double *__restrict__ samples, int ordered)
 {
     constexpr int D = SingleDims<MODEL>::D, NT = SingleDims<MODEL>::NT, NF = SingleDims<MODEL>::NF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -213,7 +275,8 @@ __global__ void __launch_bounds__(128, MINB)
     PHF_STAGE_FASTMATH_TABLE(T);
 
     const int cta_chains = blockDim.x / G;
-    const int64_t first = (int64_t)blockIdx.x * cta_chains;
+    const int64_t first = (int64_t)(ordered ? ordered_block_index(cta_chains, dataset_id, datasets, groups)
+                                            : (int)blockIdx.x) * cta_chains;  // (kernel argument: CTA-uniform)
     const int64_t chain = first + threadIdx.x / G;
     const int gl = threadIdx.x & (G - 1);
     const bool active = chain < n;
@@ -360,7 +423,9 @@ static int launch_am_single(const phf_am_config &cfg, int64_t n, int block, size
         return set_cuda_error(e, "cudaFuncSetAttribute");
     const int cta_chains = block / G;
     const unsigned grid = (unsigned)((n + cta_chains - 1) / cta_chains);
-    kern<<<grid, block, smem, s>>>(cfg, n, state, dataset_id, temperature, datasets, groups, samples);
+    // expensive chain blocks first (ordered_block_index) when there is more than one CTA per SM and one wave or so
+    const int ordered = cfg.cta_order == 0 && grid > (unsigned)sm_count() && grid <= (unsigned)kOrderMaxGrid;
+    kern<<<grid, block, smem, s>>>(cfg, n, state, dataset_id, temperature, datasets, groups, samples, ordered);
     count_launch();
     return check_launch("am_single_kernel");
 }

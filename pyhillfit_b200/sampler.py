@@ -82,7 +82,8 @@ class _Base:
                              burn_rows=int(self.burn_rows), rows_capacity=int(rows_capacity), seed=int(self.seed),
                              chain_id_base=int(self.chain_id_base), stage_groups=int(self.stage_groups),
                              block_threads=int(self.block_threads), lanes_per_chain=int(getattr(self, "lanes", 0)),
-                             min_ctas_hint=int(getattr(self, "occupancy_hint", 0)))
+                             min_ctas_hint=int(getattr(self, "occupancy_hint", 0)),
+                             cta_order=int(getattr(self, "cta_order", 0)))
 
 
 class SingleLevelSampler(_Base):

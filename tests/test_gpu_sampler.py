@@ -413,3 +413,26 @@ def test_hier_host_buffer_entry_point(table, ne, lanes):
                                   pack.datasets.ctypes.data, len(pack.points), pack.points.ctypes.data, C.byref(pr),
                                   samples.ctypes.data, 1, 0) != 0
     assert b"n_expts" in L.phf_last_error()
+
+
+@pytest.mark.parametrize("model,lanes", [(2, 2), (1, 1)])
+def test_cta_order_does_not_change_results(table, model, lanes):
+    """cfg.cta_order: chain blocks run by decreasing cost (default) or in index order -- which CTA runs a block changes
+    nothing: samples and states are bit-identical.  All 210 pairs x 24 chains = several CTAs per SM, a ragged tail."""
+    from pyhillfit_b200.packing import SinglePack
+    from pyhillfit_b200.sampler import SingleLevelSampler
+    pairs = table.pairs()
+    pack = SinglePack([table.concat(d, c) for d, c in pairs])
+    ids = np.repeat(np.arange(len(pairs), dtype=np.int32), 24)[:-5]
+    d = 2 if model == 1 else 3
+    theta0 = np.tile([5.5, 1.0, 6.0] if model == 2 else [5.5, 6.0], (len(ids), 1))
+    kw = dict(variant="fit", adapt_when=150, seed=4, thinning=5, burn_rows=0, lanes=lanes, block_threads=32)
+    a = SingleLevelSampler(model, pack, ids, 1.0, theta0, **kw)
+    b = SingleLevelSampler(model, pack, ids, 1.0, theta0, **kw)
+    b.cta_order = 1
+    ra, rb = a.run(400).cpu().numpy(), b.run(400).cpu().numpy()
+    assert ra.shape == (len(ids), 80, d + 1) and np.all(np.isfinite(ra))
+    assert np.array_equal(ra, rb)
+    assert np.array_equal(a.state.cpu().numpy(), b.state.cpu().numpy())
+    rr = a.run(200, row_major=True).cpu().numpy()          # the row-major layout goes through the same block index
+    assert np.array_equal(rr.transpose(1, 0, 2), b.run(200).cpu().numpy())
