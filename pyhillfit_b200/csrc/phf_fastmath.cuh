@@ -183,14 +183,22 @@ PHF_FM double poly(const double *c, const double *xp)
 }
 
 // ---- 1/a, a finite and normal (|a| in [1e-290, 1e290]); <= 1 ulp ---------------------------------
+// seed (relative error e0 ~ 2^-20) -> y0 (1 + e0 + e0^2) = (1 - e0^3)/a: 2^-60 before the final rounding.  (A further
+// correction step, two more instructions, only turns "within 1 ulp" into "almost always correctly rounded".)
+#ifndef PHF_FM_RCP_STEPS
+#define PHF_FM_RCP_STEPS 1
+#endif
 PHF_FM double rcp(double a)
 {
     double y = rcp_seed(a);
     double e = fma(-a, y, 1.0);
     e = fma(e, e, e);
-    y = fma(y, e, y);  // relative error ~2^-60
+    y = fma(y, e, y);
+#if PHF_FM_RCP_STEPS > 1
     e = fma(-a, y, 1.0);
-    return fma(y, e, y);
+    y = fma(y, e, y);
+#endif
+    return y;
 }
 
 // ---- 1/sqrt(a), a > 0 normal --------------------------------------------------------------------
@@ -340,12 +348,49 @@ PHF_FM double erfcx_nonneg(const double *T, double t)
     return P * (r * a);
 }
 
+#if PHF_FM_LUT
+// Table-driven form (erfcx_nonneg_pw): the same map t -> q, then one of 32 degree-7 polynomials (interval j of q, local variable
+// v = 16 q + 15.5 - j in [-1/2, 1/2]; coefficients in the shared-memory table): 9 fp64 instructions for the polynomial
+// instead of 26.  (q reaches 1 only for t >= 2^55, where the last interval's polynomial is then evaluated at the wrong
+// end: 0.4 % off, far outside every caller's range -- see above.)
+PHF_FM double erfcx_nonneg_pw(const double *T, double t)
+{
+    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+    const double a = t + PHF_ERFCX_K, b = fma(2.0, t, 1.0);
+    const double r = rcp(a * b);
+    const double q = (t - PHF_ERFCX_K) * (r * b);
+    const double s = fma(q, 0.5 * PHF_FM_LUT_ERFCX_N, 0.5 * PHF_FM_LUT_ERFCX_N - 0.5);
+    const double tt = s + kMagic;  // round to nearest: interval index in the low word
+    int j = lo_word(tt);
+    // (one unsigned compare also catches the garbage index of an out-of-domain t < 0 or NaN -- the samplers evaluate
+    // proposals with a negative sigma before they reject them -- so the table read stays inside the table)
+    j = (unsigned)j < (unsigned)PHF_FM_LUT_ERFCX_N ? j : PHF_FM_LUT_ERFCX_N - 1;
+    const double v = s - (tt - kMagic);
+    const double2 *c = reinterpret_cast<const double2 *>(lut(T) + PHF_FM_LUT_ERFCX + 8 * j);
+    const double2 c01 = c[0], c23 = c[1], c45 = c[2], c67 = c[3];
+    const double v2 = v * v, v4 = v2 * v2;
+    const double lo = fma(fma(c23.y, v, c23.x), v2, fma(c01.y, v, c01.x));
+    const double hi = fma(fma(c67.y, v, c67.x), v2, fma(c45.y, v, c45.x));
+    return fma(hi, v4, lo) * (r * a);
+}
+#else
+PHF_FM double erfcx_nonneg_pw(const double *T, double t) { return erfcx_nonneg(T, t); }
+#endif
+
 // ---- log Phi(z), z <= 0: log(erfcx(|z|/sqrt2)/2) - z^2/2 (scipy.special.log_ndtr's z < -1 branch, accurate
 //      on all of z <= 0 because the value never comes near zero there) -------------------------------
 PHF_FM double log_ndtr_nonpos(const double *T, double z)
 {
     const double t = fabs(z) * coef(T)[PHF_FM_KMISC + 2];
     return fma(-t, t, log_pos(T, 0.5 * erfcx_nonneg(T, t)));
+}
+// the same with the table-driven erfcx (measured on B200: wins when two or four lanes share a chain -- config 2
+// +7 % -- and loses with one thread per chain, where twelve warps per SM keep the shared-memory pipe busy with
+// scattered 16-byte reads: config 5 -11 %, the hierarchical thread kernel -1.5 %; so only those kernels use it)
+PHF_FM double log_ndtr_nonpos_pw(const double *T, double z)
+{
+    const double t = fabs(z) * coef(T)[PHF_FM_KMISC + 2];
+    return fma(-t, t, log_pos(T, 0.5 * erfcx_nonneg_pw(T, t)));
 }
 
 // ---- sin and cos of 2 pi b / 2^32 ---------------------------------------------------------------

@@ -15,7 +15,7 @@ struct SingleDims {
 
 // One unique dose's contribution: centred Gaussian term (sum over its 0 < y < 100 replicates) and the
 // censored terms n0 logPhi((0-p)/sigma) + n100 logPhi((p-100)/sigma)  (doseresponse.py:215-222, 241-248).
-template <int MODEL>
+template <int MODEL, bool PW = false>
 PHF_DI void dose_group_terms(const double *T, const phf_dose_group &Gd, double hill, double lic_hi, double lic_lo, double inv_ic50,
                              double inv_s, double &e2, double &cens)
 {
@@ -28,8 +28,12 @@ PHF_DI void dose_group_terms(const double *T, const phf_dose_group &Gd, double h
         // one evaluation stream serves either kind of censoring; a dose carrying both zeros and hundreds
         // (none in the Crumb table) takes the second call
         const double z = has0 ? (0.0 - p) * inv_s : (p - 100.0) * inv_s;  // st.norm.logcdf(0,p,s) / logsf(100,p,s)
-        cens = fma(has0 ? Gd.n0 : Gd.n100, log_ndtr_nonpos(T, z), cens);
-        if (has0 && has100) cens = fma(Gd.n100, log_ndtr_nonpos(T, (p - 100.0) * inv_s), cens);
+        // (PW: see censored_pair -- one kernel uses one form of erfcx throughout, or it carries the code of both)
+        cens = fma(has0 ? Gd.n0 : Gd.n100, PW ? fm::log_ndtr_nonpos_pw(T, z) : fm::log_ndtr_nonpos(T, z), cens);
+        if (has0 && has100) {
+            const double z2 = (p - 100.0) * inv_s;
+            cens = fma(Gd.n100, PW ? fm::log_ndtr_nonpos_pw(T, z2) : fm::log_ndtr_nonpos(T, z2), cens);
+        }
     }
 }
 
@@ -37,9 +41,11 @@ PHF_DI void dose_group_terms(const double *T, const phf_dose_group &Gd, double h
 // VOTE = true (sampler kernels: every lane of the warp is alive and converged): the warp decides by vote whether
 // it needs the two-term path (both evaluations interleaved in one instruction stream), the one-term path or
 // none, so a warp whose chains share a censoring pattern never executes more evaluations than it needs.
-template <bool VOTE>
+// PW: the table-driven erfcx (fm::log_ndtr_nonpos_pw) -- the kernels in which lanes share a chain.
+template <bool VOTE, bool PW = false>
 PHF_DI double censored_pair(const double *T, double z0, double w0, double z1, double w1)
 {
+    auto lphi = [&](double z) { return PW ? fm::log_ndtr_nonpos_pw(T, z) : fm::log_ndtr_nonpos(T, z); };
     const bool c0 = w0 > 0.0, c1 = w1 > 0.0;
     bool two = c0 && c1, one = c0 || c1;
     if (VOTE) {
@@ -48,9 +54,9 @@ PHF_DI double censored_pair(const double *T, double z0, double w0, double z1, do
     }
     double acc = 0.0;
     if (two) {
-        acc = fma(w1, log_ndtr_nonpos(T, z1), w0 * log_ndtr_nonpos(T, z0));
+        acc = fma(w1, lphi(z1), w0 * lphi(z0));
     } else if (one) {
-        acc = (c0 ? w0 : w1) * log_ndtr_nonpos(T, c0 ? z0 : z1);
+        acc = (c0 ? w0 : w1) * lphi(c0 ? z0 : z1);
     }
     return acc;
 }
@@ -102,6 +108,7 @@ PHF_DI void single_log_target_lanes(const double *T, const double *th, const phf
         inv_ic50 = fm::exp10_clamped(T, pic50 - 6.0);  // 1/IC50, IC50 = 10**(6-pIC50) (doseresponse.py:87-88)
 
     constexpr int U = 4 / G;
+    constexpr bool PW = VOTE && G >= 2;  // table-driven erfcx in the sampler kernels whose lanes share a chain
     double e2 = 0.0, cens = 0.0;
     double zc[U], wc[U], pu[U];
     bool both_kinds = false;
@@ -126,22 +133,23 @@ PHF_DI void single_log_target_lanes(const double *T, const double *th, const phf
         both_kinds = both_kinds || (has0 && has100);
     }
     if (U == 1) {
-        cens = censored_pair<VOTE>(T, zc[0], wc[0], zc[0], 0.0);
+        cens = censored_pair<VOTE, PW>(T, zc[0], wc[0], zc[0], 0.0);
     } else {
 #pragma unroll
-        for (int u = 0; u + 1 < U; u += 2) cens += censored_pair<VOTE>(T, zc[u], wc[u], zc[u + 1], wc[u + 1]);
+        for (int u = 0; u + 1 < U; u += 2) cens += censored_pair<VOTE, PW>(T, zc[u], wc[u], zc[u + 1], wc[u + 1]);
     }
     if (both_kinds) {  // a dose carrying zeros AND hundreds (none in the Crumb table): its second term
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int g = gl + u * G;
             if (g < ng && grp[g].n0 > 0.0 && grp[g].n100 > 0.0)
-                cens = fma(grp[g].n100, log_ndtr_nonpos(T, (pu[u] - 100.0) * inv_s), cens);
+                cens = fma(grp[g].n100, PW ? fm::log_ndtr_nonpos_pw(T, (pu[u] - 100.0) * inv_s)
+                                           : fm::log_ndtr_nonpos(T, (pu[u] - 100.0) * inv_s), cens);
         }
     }
     for (int g = gl + U * G; g < ng; g += G) {  // designs with more than four unique doses
         const phf_dose_group Gd = grp[g];
-        dose_group_terms<MODEL>(T, Gd, hill, lic_hi, lic_lo, inv_ic50, inv_s, e2, cens);
+        dose_group_terms<MODEL, PW>(T, Gd, hill, lic_hi, lic_lo, inv_ic50, inv_s, e2, cens);
     }
     // cens - pi_bit - n_other ln(sigma) - e2 / (2 sigma^2)   (doseresponse.py:220-222, 246-248)
     double raw, log_sm4;

@@ -74,13 +74,14 @@ def test_rcp_rsqrt_sqrt(L):
     assert call(L, "fmh_sqrt", np.array([0.0]))[0] == 0.0
 
 
-def test_erfcx_and_log_ndtr(L):
+@pytest.mark.parametrize("suffix", ["", "_pw"])   # the one-polynomial form and the table-driven (piecewise) one
+def test_erfcx_and_log_ndtr(L, suffix):
     rng = np.random.default_rng(3)
     t = np.concatenate([rng.uniform(0, 10, 4000), np.exp(rng.uniform(np.log(1e-8), np.log(1e6), 3000)), [0.0]])
-    got, want = call(L, "fmh_erfcx", t), exact(lambda v: mp.exp(v * v) * mp.erfc(v), t)
+    got, want = call(L, "fmh_erfcx" + suffix, t), exact(lambda v: mp.exp(v * v) * mp.erfc(v), t)
     assert np.max(np.abs(got - want) / want) <= 2e-15
     z = -np.concatenate([rng.uniform(0, 40, 4000), np.exp(rng.uniform(np.log(1e-8), np.log(1e5), 2000)), [0.0]])
-    got, want = call(L, "fmh_log_ndtr", z), exact(lambda v: mp.log(mp.ncdf(v)), z)
+    got, want = call(L, "fmh_log_ndtr" + suffix, z), exact(lambda v: mp.log(mp.ncdf(v)), z)
     assert np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))) <= 3e-15
 
 
