@@ -202,14 +202,25 @@ PHF_FM double rcp(double a)
 }
 
 // ---- 1/sqrt(a), a > 0 normal --------------------------------------------------------------------
+// One third-order step from the seed y0 = (1 + d)/sqrt(a), |d| ~ 2^-20: e = (1 - a y0^2)/2 = -d - d^2/2 and
+// y0 (1 + e + 3/2 e^2) = (1 + O(d^3))/sqrt(a).  Five instructions with a dependent chain of four (two second-order
+// steps: six and six) -- the three rsqrt of the proposal's Cholesky factor are the head of every iteration's chain.
+#ifndef PHF_FM_CUBIC_ROOTS
+#define PHF_FM_CUBIC_ROOTS 1
+#endif
 PHF_FM double rsqrt(double a)
 {
     double y = rsqrt_seed(a);
     const double h = 0.5 * a;
+#if PHF_FM_CUBIC_ROOTS
+    const double e = fma(-(h * y), y, 0.5);
+    return fma(y * e, fma(1.5, e, 1.0), y);
+#else
     double e = fma(-(h * y), y, 0.5);
     y = fma(y, e, y);
     e = fma(-(h * y), y, 0.5);
     return fma(y, e, y);
+#endif
 }
 
 // ---- sqrt(a), a >= 0 (a == 0 -> 0) --------------------------------------------------------------
@@ -217,11 +228,16 @@ PHF_FM double sqrt_nonneg(double a)
 {
     const double y = rsqrt_seed(fmax(a, 1e-290));
     double g = a * y, h = 0.5 * y;
+#if PHF_FM_CUBIC_ROOTS
+    const double r = fma(-h, g, 0.5);            // (1 - a y^2)/2
+    return fma(g * r, fma(1.5, r, 1.0), g);      // g (1 + r + 3/2 r^2)
+#else
     double r = fma(-h, g, 0.5);
     g = fma(g, r, g);
     h = fma(h, r, h);
     r = fma(-h, g, 0.5);
     return fma(g, r, g);
+#endif
 }
 
 // ---- exp(x); the argument is clamped to [-700, 700] (the callers' results saturate long before) -----
