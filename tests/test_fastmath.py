@@ -107,3 +107,43 @@ def test_sincos_of_a_32_bit_turn(L):
     L.fmh_sincos(C.c_int(len(b)), b2.ctypes.data_as(C.c_void_p), s2.ctypes.data_as(C.c_void_p),
                  c2.ctypes.data_as(C.c_void_p))
     assert np.array_equal(s2, -s) and np.array_equal(c2, -c)
+
+
+def test_table_driven_functions_at_the_edges(L):
+    """Interval boundaries of the lookup tables, the ends of the domains, and out-of-domain arguments (which the
+    samplers do produce -- a proposal with a negative sigma is evaluated before it is rejected -- and which must
+    come back as some finite-or-NaN number without reading outside the table)."""
+    # log: every table interval's first and last double, the smallest / largest normal numbers
+    hi = (0x3fe6a09e + np.arange(129, dtype=np.int64) * 8192) << 32
+    edges = np.concatenate([hi.view(np.float64), np.nextafter(hi.view(np.float64), 0), [2.0 ** -1022, 1.7e308]])
+    got, want = call(L, "fmh_log", edges), exact(mp.log, edges)
+    far = np.abs(want) >= 2.0 ** -7
+    assert np.max(np.abs(got - want)[far] / np.spacing(np.abs(want[far]))) <= 2
+    assert np.max(np.abs(got - want)[~far]) <= 1.5e-18
+    # exp: multiples of ln2/64 (interval boundaries of the reduction) and the clamp
+    k = np.arange(-64000, 64001, 997)
+    x = np.concatenate([k * (np.log(2) / 64), (k + 0.5) * (np.log(2) / 64), [700.0, -700.0, 699.999, -699.999]])
+    assert ulps(call(L, "fmh_exp", x), exact(mp.exp, x)) <= 2
+    # erfcx (both forms): boundaries of the 32 intervals of q = (t - 4)/(t + 4), t = 0, large t
+    q = -1 + np.arange(1, 32) / 16.0
+    t = np.concatenate([4 * (1 + q) / (1 - q), [0.0, 1e3, 7.1e4, 1e10]])
+    t = np.concatenate([t, np.nextafter(t, 0), np.nextafter(t, np.inf)])
+    t = t[t >= 0]
+    want = exact(lambda v: mp.exp(v * v) * mp.erfc(v), t)
+    for name in ("fmh_erfcx", "fmh_erfcx_pw"):
+        assert np.max(np.abs(call(L, name, t) - want) / want) <= 2e-15
+    bad = call(L, "fmh_erfcx_pw", np.array([-1.0, -4.0, -1e300, np.nan, np.inf]))
+    assert bad.shape == (5,)            # no crash, whatever the values
+
+
+def test_lookup_table_file_is_what_the_generator_writes(tmp_path):
+    """pyhillfit_b200/csrc/phf_fastmath_lut.inc is generated (scripts/gen_fastmath_lut.py): regenerate and compare."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_fastmath_lut", os.path.join(HERE, "..", "scripts",
+                                                                                   "gen_fastmath_lut.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = tmp_path / "lut.inc"
+    mod.main(str(out))
+    committed = open(os.path.join(HERE, "..", "pyhillfit_b200", "csrc", "phf_fastmath_lut.inc")).read()
+    assert out.read_text() == committed
