@@ -211,7 +211,8 @@ int phf_hier_predictive_cdfs(int64_t n_rows, const double *rows, int32_t row_str
  * Host-buffer entry point (the reference-facing call: numpy arrays in, numpy arrays out).
  * Every pointer is a HOST pointer (pinned memory makes the copies asynchronous).  One call = copy state
  * and data to the device, run cfg->n_iters iterations in `n_segments` launches whose sample write-back
- * overlaps the next launch, copy state and samples back, synchronise.  `device` selects the GPU.
+ * overlaps the next launch, copy state and samples back, synchronise.  `device` selects the GPU (the calling thread's
+ * current device is left as it was).
  * ---------------------------------------------------------------------------------------------- */
 int phf_am_single_run_host(const phf_am_config *cfg, int64_t n_chains, double *state, const int32_t *dataset_id,
                            const double *temperature, int32_t n_datasets, const phf_dataset *datasets,

@@ -35,6 +35,21 @@ struct Workspace {
 Workspace g_ws[16][2];  // [device][model-1]: the two models may be driven from two host threads
 Workspace g_ws_hier[16][8];  // [device][min(n_expts, 7)]: launches of different dimension may be driven concurrently
 
+// The entry points run on `device` and leave the calling thread's current device as they found it.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t enter(int device)
+    {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) { prev = -1; return e; }
+        return prev == device ? cudaSuccess : cudaSetDevice(device);
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 int ensure_streams(Workspace &w)
 {
     if (w.init) return PHF_OK;
@@ -128,7 +143,8 @@ extern "C" int phf_am_single_run_host(const phf_am_config *cfg, int64_t n_chains
     if (n_segments < 1) n_segments = 1;
     const int d = cfg->model == 1 ? 2 : 3, nf = PHF_STATE_SIZE(d);
     cudaError_t e;
-    if ((e = cudaSetDevice(device))) return set_cuda_error(e, "cudaSetDevice");
+    DeviceGuard guard;
+    if ((e = guard.enter(device))) return set_cuda_error(e, "cudaSetDevice");
     Workspace &w = g_ws[device][cfg->model - 1];
     if (int rc = ensure_streams(w)) return rc;
     const uint32_t rows_total = (cfg->t0 + cfg->n_iters) / cfg->thinning - cfg->t0 / cfg->thinning;
@@ -174,7 +190,8 @@ extern "C" int phf_am_hier_run_host(const phf_am_config *cfg, int32_t n_expts, i
     if (n_segments < 1) n_segments = 1;
     const int d = 5 + 2 * n_expts, nf = PHF_STATE_SIZE(d);
     cudaError_t e;
-    if ((e = cudaSetDevice(device))) return set_cuda_error(e, "cudaSetDevice");
+    DeviceGuard guard;
+    if ((e = guard.enter(device))) return set_cuda_error(e, "cudaSetDevice");
     Workspace &w = g_ws_hier[device][n_expts < 7 ? n_expts : 7];
     if (int rc = ensure_streams(w)) return rc;
     const uint32_t rows_total = (cfg->t0 + cfg->n_iters) / cfg->thinning - cfg->t0 / cfg->thinning;
