@@ -71,10 +71,14 @@ struct Philox4 {
     uint32_t w[4];
 };
 
+// (PHF_PHILOX_ROUNDS: a measurement knob only -- the stream contract, the oracle and every trajectory test are 10 rounds)
+#ifndef PHF_PHILOX_ROUNDS
+#define PHF_PHILOX_ROUNDS 10
+#endif
 PHF_DI Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < PHF_PHILOX_ROUNDS; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         c0 = hi1 ^ c1 ^ k0;
