@@ -436,8 +436,13 @@ def main():
         traffic = tr["dram_bytes_per_chain_iteration"] * n_chains * K * (bytes_iter / 6.4)
     except Exception:
         pass
+    ncu_util = None
+    try:   # FP64-pipe and issue-slot utilisation of this kernel from the committed `ncu --set full` captures
+        ncu_util = json.load(open(os.path.join(ROOT, "profiles", "pipe_utilisation.json")))
+    except Exception:
+        pass
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                "traffic": traffic,
+                "traffic": traffic, "ncu": ncu_util,
                 "kernel": "am_single_kernel<model 1 | model 2, %d lanes per chain> (two co-resident launches per step)"
                           % samplers[2].lanes,
                 "launch_ms": ms / args.steps, "launch_ms_on_stream": launch_ms_timed,
