@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            (under torchrun for N > 1)
     python bench.py --impl reference ...                      (CPU arm: the reference's algorithm on host cores)
 
-Workload (BASELINE.json configs[1]): every Crumb (drug, channel) pair (210) x single-level models {1, 2} x 64
+Headline workload (BASELINE.json configs[1]): every Crumb (drug, channel) pair (210) x single-level models {1, 2} x 64
 chains = 26 880 chains per GPU, PyHillFit-variant adaptive Metropolis (python/PyHillFit.py:828-856), thinning 5.
 One step = `--iters-per-step` iterations of every chain (two kernel launches, one per model, on two streams),
 thinned samples written to HBM.  N > 1: every rank runs the same workload with disjoint Philox chain ids (weak
@@ -13,9 +13,17 @@ scaling, no collective on the data path); the value is chains x iterations over 
 The JSON line carries: value (device-timed, inputs resident), e2e (through phf_am_single_run_host with pinned
 host buffers, H2D of state+data and D2H of samples+state inside the timed region), roofline (FP64: algorithmic
 flops W per chain-iteration from SURVEY.md section 8d / the live DFMA probe), cpu_baseline (the oracle's numpy/scipy
-restatement of the reference loop on all host cores, bounded sample), clocks, gpu_launches, ess_per_s.
+restatement of the reference loop on all host cores, bounded sample, with ESS/s by the same estimator), clocks,
+gpu_launches, ess_per_s, and `other_configs`:
+  * at every N, the north-star's STRONG-scaling workloads, sharded over the N ranks (python/PyHillTemp.py:151-161,
+    python/compute_bayes_factors.py:77-100): the reference's whole thermodynamic-integration sweep (41 temperatures x
+    210 pairs x 2 models x 500 000 iterations), BASELINE config 4 (64 temperatures) -- NCCL all-gather of the per-chain
+    mean log-likelihoods and the trapezium rule INSIDE the timed region -- and BASELINE config 5 (10^6 synthetic
+    datasets x 4 chains); each with its own FP64 roofline entry;
+  * at N = 1 also BASELINE config 3 (hierarchical).
 """
 import argparse
+import hashlib
 import json
 import math
 import multiprocessing as mp
@@ -46,23 +54,40 @@ def emit(line):
 METRIC = "chain-iterations/sec (all chains, device-timed)"
 UNIT = "chain-iterations/s"
 WORKLOAD = "Crumb: 210 drug-channel pairs x single-level models {1,2} x %d chains, PyHillFit AM, thinning %d"
+DATA = ("real: the Crumb et al. dose-response table the reference ships (data/crumb_data.csv, packaged as "
+        "tests/golden/datasets.npz); chains start at the least-squares fit (chains 1..63 of a pair jittered by 2 %); "
+        "config 5 in other_configs is synthetic (pyhillfit_b200/synthetic.py)")
 
 
 # ----------------------------------------------------------------------------------------------
 # algorithmic FP64 work per chain-iteration (SURVEY.md section 8d cost table; FMA = 2 flops)
 # ----------------------------------------------------------------------------------------------
-def flops_per_iteration(model, groups):
+def flops_per_iteration(model, groups, prior_only=False):
     d = 2 if model == 1 else 3
     D = len(groups)
     d_other = int(np.count_nonzero(groups["n_other"] > 0))
     d_cens = int(np.count_nonzero(groups["n0"] > 0) + np.count_nonzero(groups["n100"] > 0))
     per_dose = 53 if model == 2 else 52
-    lik = 40 + 58 + D * per_dose + d_other * 5 + d_cens * 133 + 6
+    lik = 0 if prior_only else 40 + 58 + D * per_dose + d_other * 5 + d_cens * 133 + 6   # t == 0: doseresponse.py:204-205
     prior = 56
     proposal = math.ceil(d / 2) * 118 + d * (d + 1) + d + 40
     accept = 53
     adapt = 3 * d * d + 16 * d + 4 * d + 3
     return lik + prior + proposal + accept + adapt
+
+
+def hier_flops_per_iteration(n_expts, n_points):
+    """SURVEY.md section 8d, hierarchical: per point Hill curve + 2 erfc + log = 271, per experiment ~330 (logistic +
+    log-logistic terms), 5 Gamma hyper-priors, proposal / accept / adapt as for the single-level loop at dimension d
+    (6.1 kflops at Ne = 3, N = 12)."""
+    d = 5 + 2 * n_expts
+    return (271 * n_points + 330 * n_expts + 5 * 56 + math.ceil(d / 2) * 118 + d * (d + 1) + d + 40 + 53 +
+            3 * d * d + 16 * d + 4 * d + 3)
+
+
+def pack_flops(model, pack):
+    return np.array([flops_per_iteration(model, pack.groups[b:b + n]) for b, n in
+                     zip(pack.datasets["group_begin"], pack.datasets["n_groups"])], dtype=float)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -77,7 +102,7 @@ def build_workload(chains_per_pair):
     data = [table.concat(d, c) for d, c in pairs]
     pack = SinglePack(data)
     rng = np.random.default_rng(25)
-    out = {}
+    out = {"data": data}
     for model in (1, 2):
         d = 2 if model == 1 else 3
         fits = best_fit_batch(model, data)[0]
@@ -90,9 +115,9 @@ def build_workload(chains_per_pair):
             theta0[:, 1] = np.clip(theta0[:, 1], 1e-6, 10.0)
         theta0[:, 0] = np.maximum(theta0[:, 0], -3.0)
         ids = np.repeat(np.arange(len(pairs), dtype=np.int32), chains_per_pair)
-        w = np.array([flops_per_iteration(model, pack.groups[b:b + n]) for b, n in
-                      zip(pack.datasets["group_begin"], pack.datasets["n_groups"])], dtype=float)
-        out[model] = dict(theta0=theta0, ids=ids, d=d, flops=float(np.repeat(w, chains_per_pair).mean()))
+        w = pack_flops(model, pack)
+        out[model] = dict(theta0=theta0, ids=ids, d=d, flops=float(np.repeat(w, chains_per_pair).mean()),
+                          flops_per_dataset=w)
     return pack, out
 
 
@@ -149,10 +174,12 @@ class Clocks:
 # CPU arms
 # ----------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    """One chain of the reference loop (numpy/scipy restatement, numpy RNG) -- returns seconds for `iters`."""
+    """One chain of the reference loop (numpy/scipy restatement, numpy RNG) -- returns (seconds for `iters`, the
+    min-over-parameters Geyer ESS of the run's post-burn rows: the same estimator as the GPU arm's ess_per_s)."""
     model, concs, y, theta0, warm, iters, seed = args
     import numpy.random as npr
     import hill_oracle as ho
+    from pyhillfit_b200.ess import ess_min
     w0, w100, wo = ho.masks(y)
     pb = ho.compute_pi_bit_of_log_likelihood(wo)
 
@@ -163,12 +190,15 @@ def _cpu_worker(args):
     with np.errstate(all="ignore"):
         ho.adaptive_metropolis(target, theta0, warm, 5, "fit", rng="numpy")
         t0 = time.perf_counter()
-        ho.adaptive_metropolis(target, theta0, iters, 5, "fit", rng="numpy")
-        return time.perf_counter() - t0
+        chain, _ = ho.adaptive_metropolis(target, theta0, iters, 5, "fit", rng="numpy")
+        dt = time.perf_counter() - t0
+    d = len(theta0)
+    post = chain[len(chain) // 4:, :d]            # burn-in removed as PyHillFit.py:861-864 does
+    return dt, ess_min(post) * len(chain) / max(len(post), 1)   # ESS of the post-burn rows scaled to the whole run
 
 
 def cpu_reference_rate(iters, warm=500, cores=None, spread=False):
-    """chain-iterations/s of the reference algorithm (oracle port) with one chain per host core.
+    """chain-iterations/s and ESS/s of the reference algorithm (oracle port) with one chain per host core.
     spread=False: every core runs Amiodarone/hERG model 2 (BASELINE configs[0]); spread=True: core k runs pair
     17k mod 210 and models alternate, a sample of the config-2 workload."""
     from _data import Table
@@ -186,9 +216,10 @@ def cpu_reference_rate(iters, warm=500, cores=None, spread=False):
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        secs = pool.map(_cpu_worker, jobs)
+        res = pool.map(_cpu_worker, jobs)
     wall = time.perf_counter() - t0
-    return cores * iters / max(secs), cores, wall
+    slowest = max(r[0] for r in res)
+    return cores * iters / slowest, cores, wall, float(sum(r[1] for r in res)) / slowest
 
 
 def cpu_c_port_rate(seconds=2.0):
@@ -220,14 +251,15 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     per_step = max(200, args.ref_iters_per_step)
-    rates = []
+    rates, ess = [], []
     cores = mp.cpu_count()
     for _ in range(args.warmup):
         cpu_reference_rate(max(100, per_step // 10), warm=50, spread=True)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r, cores, _ = cpu_reference_rate(per_step, warm=100, spread=True)
+        r, cores, _, e = cpu_reference_rate(per_step, warm=100, spread=True)
         rates.append(r)
+        ess.append(e)
     wall = time.perf_counter() - t0
     value = float(np.mean(rates))
     sample = ("%d chains (one per host core) x %d iterations per step of the PyHillFit single-level AM loop "
@@ -235,9 +267,15 @@ def run_reference_arm(args):
               "core k runs Crumb pair 17k mod 210, models 1 and 2 alternate" % (cores, per_step))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": DATA,
             "config": {"workload": WORKLOAD % (args.chains_per_pair, 5), "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "ess_per_s": float(np.mean(ess))},
+            "ess_per_s": float(np.mean(ess)),
+            "ess_note": "Geyer initial-positive-sequence ESS (pyhillfit_b200/ess.py), min over parameters, post-burn rows "
+                        "of each step's chains, summed over chains / seconds -- the estimator of the GPU arm's ess_per_s; "
+                        "a %d-iteration chain has barely started adapting (adaptation begins at 1000 d), so this is an "
+                        "early-chain figure" % per_step,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -247,6 +285,11 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+class Ctx:
+    """what the sections below share"""
+    pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -257,16 +300,20 @@ def main():
     ap.add_argument("--chains-per-pair", type=int, default=64)
     ap.add_argument("--thinning", type=int, default=5)
     ap.add_argument("--ref-iters-per-step", type=int, default=4000)
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--e2e-segments", type=int, default=32)
-    ap.add_argument("--e2e-layout", default="row", choices=["row", "chain"],
-                    help="sample layout of the end-to-end call: row = [row][chain][d+1] (contiguous transfers)")
-    ap.add_argument("--layout", default="chain", choices=["row", "chain"], help="sample layout of the device-timed step")
+    ap.add_argument("--layout", default="row", choices=["row", "chain"],
+                    help="sample layout of the device-timed step AND of the end-to-end call: row = [row][chain][d+1] "
+                         "(coalesced write-out, contiguous transfers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--no-stage", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the sharded TI sweeps / config 5")
+    ap.add_argument("--ti-iterations", type=int, default=500000, help="iterations of the TI sweeps (reference default)")
+    ap.add_argument("--config5-datasets", type=int, default=1000000)
+    ap.add_argument("--config5-iters", type=int, default=1000)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per chain (0: library default)")
     ap.add_argument("--occupancy-hint", type=int, default=0, help="developer knob: min CTAs/SM variant")
     ap.add_argument("--cta-order", type=int, default=0, help="developer knob: 0 chain blocks by decreasing cost, 1 index order")
@@ -291,11 +338,19 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        # each rank's host threads (the end-to-end calls, the pinned-buffer copies) stay on their own slice of the cores
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(len(cores) // world, 1)
+            os.sched_setaffinity(0, cores[local * per:(local + 1) * per] or cores)
+        except Exception:
+            pass
 
     pack, wl = build_workload(args.chains_per_pair)
     thin = args.thinning
     K = args.iters_per_step
     rows_per_step = K // thin
+    row_major = args.layout == "row"
     samplers, buffers, streams = {}, {}, {}
     n_chains = 0
     for model in (1, 2):
@@ -309,12 +364,13 @@ def main():
         s.occupancy_hint = args.occupancy_hint
         s.cta_order = args.cta_order
         samplers[model] = s
-        buffers[model] = torch.empty((rows_per_step + 1, n, w["d"] + 1) if args.layout == "row" else
+        buffers[model] = torch.empty((rows_per_step + 1, n, w["d"] + 1) if row_major else
                                      (n, rows_per_step + 1, w["d"] + 1), dtype=torch.float64, device=dev)
         streams[model] = torch.cuda.Stream(device=dev)
         n_chains += n
     flops_iter = sum(wl[m]["flops"] * len(wl[m]["ids"]) for m in (1, 2)) / n_chains
     bytes_iter = sum((wl[m]["d"] + 1) * 8.0 / thin * len(wl[m]["ids"]) for m in (1, 2)) / n_chains
+    e2e_state0 = {m: samplers[m].state.cpu() for m in (1, 2)}    # the start state of a complete run (for run_e2e)
 
     main_stream = torch.cuda.current_stream(dev)
     stream_events = None
@@ -322,7 +378,7 @@ def main():
     def step():
         if args.serial_models:
             for model in (2, 1):
-                samplers[model].run(K, samples=buffers[model], row_major=args.layout == "row")
+                samplers[model].run(K, samples=buffers[model], row_major=row_major)
             return
         ev = torch.cuda.Event()
         ev.record(main_stream)
@@ -333,7 +389,7 @@ def main():
                 if stream_events is not None:   # per-launch duration on the launching stream
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a.record(st)
-                samplers[model].run(K, samples=buffers[model], row_major=args.layout == "row")
+                samplers[model].run(K, samples=buffers[model], row_major=row_major)
                 if stream_events is not None:
                     b.record(st)
                     stream_events[model].append((a, b))
@@ -345,6 +401,13 @@ def main():
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(args.warmup):
         step()
@@ -370,10 +433,7 @@ def main():
     stream_events = None
     launches = _lib.launch_count() - launches0
     clk = clocks.stop(t_begin, t_end) if rank == 0 else None
-    if world > 1:
-        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+    ms = max_over_ranks(ms)
     total_iters = float(n_chains) * K * args.steps * world
     value = total_iters / (ms * 1e-3)
 
@@ -383,12 +443,12 @@ def main():
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(dev)
         a.record(main_stream)
-        samplers[model].run(K, samples=buffers[model], row_major=args.layout == "row")
+        samplers[model].run(K, samples=buffers[model], row_major=row_major)
         b.record(main_stream)
         torch.cuda.synchronize(dev)
         kern_ms[model] = a.elapsed_time(b)
 
-    # ---- ESS/s from the last written step (512 chains sampled, min over parameters, Geyer IPS) ----
+    # ---- ESS/s from the last written step (256 chains per model sampled, min over parameters, Geyer IPS) ----
     ess_per_s = None
     acc = None
     if rank == 0:
@@ -398,17 +458,27 @@ def main():
         for model in (1, 2):
             n = samplers[model].n
             pick = rng.choice(n, size=min(256, n), replace=False)
-            by_chain = buffers[model].transpose(0, 1) if args.layout == "row" else buffers[model]
+            by_chain = buffers[model].transpose(0, 1) if row_major else buffers[model]
             smp = by_chain[torch.as_tensor(pick, device=dev)][:, :rows_per_step, :wl[model]["d"]].cpu().numpy()
             per_row.append(np.mean([ess_min(c) for c in smp]) / rows_per_step)
         rows_per_s = value / thin
         ess_per_s = float(np.mean(per_row) * rows_per_s)
         acc = float(np.mean([samplers[m].acceptance().mean() for m in (1, 2)]))
 
+    cx = Ctx()
+    cx.args, cx.torch, cx.dist, cx.dev, cx.pack, cx.wl, cx.rank, cx.world, cx.local = args, torch, dist, dev, pack, wl, rank, world, local
+    cx.barrier, cx.max_over_ranks, cx.samplers = barrier, max_over_ranks, samplers
+
     # ---- end to end through the host-buffer C ABI (pinned host memory) ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, torch, dev, pack, wl, samplers, rank, world, dist)
+        e2e = run_e2e(cx, e2e_state0)
+    del buffers
+
+    # ---- the north-star's strong-scaling workloads, sharded over the ranks ----
+    strong = None
+    if not args.no_strong and not args.no_other_configs:
+        strong = strong_configs(cx)
 
     if rank != 0:
         if world > 1:
@@ -447,7 +517,8 @@ def main():
                           % samplers[2].lanes,
                 "launch_ms": ms / args.steps, "launch_ms_on_stream": launch_ms_timed,
                 "flops_per_chain_iteration": flops_iter,
-                "peak_source": "phf_fp64_peak_probe (live DFMA microbenchmark; MEASURED_PEAKS.json has no FP64 entry)",
+                "peak_source": "phf_fp64_peak_probe (live DFMA microbenchmark; MEASURED_PEAKS.json has no FP64 entry; "
+                               "ncu FP64-pipe page of the probe kernel: profiles/r02_fp64_peak_probe_ncu.txt)",
                 "algorithmic_bytes": n_chains * K * bytes_iter,
                 "model2_launch_alone": {"launch_ms": kern_ms[2], "achieved": alone_tf, "frac": alone_tf / peak_tf,
                                         "flops_per_chain_iteration": wl[2]["flops"]},
@@ -456,32 +527,47 @@ def main():
                         "algorithmic_bytes_per_chain_iteration": bytes_iter}}
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        r, cores, wall = cpu_reference_rate(6000, warm=300)
+        r, cores, wall, cpu_ess = cpu_reference_rate(6000, warm=300)
         rc, _ = cpu_c_port_rate()
         cpu_baseline = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "%d chains (one per host core) x 6000 iterations of the reference's single-level AM "
                                   "loop, numpy/scipy restatement (oracle/hill_oracle.py), Amiodarone/hERG model 2; "
                                   "%.1f s wall" % (cores, wall),
+                        "ess_per_s": cpu_ess,
+                        "ess_note": "same Geyer estimator as the GPU arm's ess_per_s (pyhillfit_b200/ess.py), min over "
+                                    "parameters, post-burn rows, summed over the chains / seconds",
                         "c_port_value": rc,
                         "c_port_note": "same loop in plain C (oracle/hill_oracle.c, Philox RNG) on all cores"}
-    other = None
+    other = {}
+    if strong:
+        for k, v in strong.items():
+            if "flops_per_chain_iteration" in v:
+                tf = v["value"] * v["flops_per_chain_iteration"] / 1e12
+                v["roofline"] = {"bound": "fp64", "achieved": tf, "peak": peak_tf * world, "unit": "TFLOP/s",
+                                 "frac": tf / (peak_tf * world), "flops_per_chain_iteration": v["flops_per_chain_iteration"]}
+            other[k] = v
     if world == 1 and not args.no_other_configs:
-        other = other_configs(torch, dev, pack)
+        c3 = config3(cx)
+        for k, v in c3.items():
+            tf = v["value"] * v["flops_per_chain_iteration"] / 1e12
+            v["roofline"] = {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                             "flops_per_chain_iteration": v["flops_per_chain_iteration"]}
+            other[k] = v
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64", "data": DATA,
             "config": {"workload": WORKLOAD % (args.chains_per_pair, thin), "chains_per_gpu": n_chains,
-                       "iters_per_step": K, "sample_layout": args.layout + "-major", "theta0": "host least-squares fit; chains 1..63 of a pair jittered by 2%",
+                       "iters_per_step": K, "sample_layout": args.layout + "-major (value and e2e alike)",
+                       "theta0": "host least-squares fit; chains 1..63 of a pair jittered by 2%",
                        "l2": "each step writes %.2f GB of thinned samples (> 126 MB L2); chain state is register-"
                              "resident, packed data (54 KB) is staged in shared memory" %
-                             (sum(buffers[m].numel() * rows_per_step // (rows_per_step + 1) for m in (1, 2)) * 8 / 1e9),
-                       "data_source": "Crumb et al. dose-response table (tests/golden/datasets.npz), random-start chains",
+                             (n_chains * K * bytes_iter / 1e9),
                        "target_1e10_frac": value / world / 1e10},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk, "ess_per_s": ess_per_s, "mean_acceptance": acc,
             "hbm_bytes_per_chain_iteration": bytes_iter, "flops_per_chain_iteration": flops_iter,
             "kernel_ms": {"am_single_kernel<1>": kern_ms[1], "am_single_kernel<2>": kern_ms[2]},
-            "other_configs": other}
+            "other_configs": other or None}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -502,51 +588,106 @@ def _timed(torch, fn, reps=3):
     return best * 1e-3
 
 
-def other_configs(torch, dev, pack):
-    """Device-timed throughput of BASELINE configs 3, 4 and one GPU's share of config 5 (context, not the headline;
-    each is one kernel launch timed alone, samples written, best of 3)."""
-    from _data import Table
+# ----------------------------------------------------------------------------------------------
+# strong scaling: the whole job is fixed, the ranks shard it
+# ----------------------------------------------------------------------------------------------
+def strong_configs(cx):
+    """The north-star's multi-GPU workloads, each a FIXED total job sharded over the ranks (`scaling: strong`):
+      * the reference's thermodynamic-integration sweep -- 41 temperatures (python/PyHillTemp.py:151) x 210 pairs x
+        models {1, 2} x `--ti-iterations` iterations -- and BASELINE config 4 (64 temperatures), through ti.run_ti: chains
+        sharded contiguously by cost, no collective while sampling, then ONE all-gather per model of the per-chain mean
+        temperature-1 log-likelihoods (NCCL) and the trapezium rule (compute_bayes_factors.py:77-100).  The timed region
+        (CUDA events on the launching stream, max over ranks) covers sampling + all-gather + integration; the NCCL
+        communicator is brought up by the warm-up call;
+      * BASELINE config 5: 10^6 synthetic datasets x 4 chains, model 2, samples written to HBM."""
+    torch, dist, dev, world, rank = cx.torch, cx.dist, cx.dev, cx.world, cx.rank
     from pyhillfit_b200 import synthetic, ti
-    from pyhillfit_b200.packing import HierPack, SinglePack
-    from pyhillfit_b200.sampler import HierarchicalSampler, SingleLevelSampler, hier_priors
+    from pyhillfit_b200.packing import SinglePack
+    from pyhillfit_b200.sampler import SingleLevelSampler
+    args, pack, data = cx.args, cx.pack, cx.wl["data"]
     out = {}
-    # config 4: PyHillTemp variant, 64 temperatures x 210 pairs x models 1, 2
-    temps = (np.arange(64.) / 63) ** 3
-    ids, tt = ti.build_chain_list(pack.n_datasets, temps, 1)
-    K = 5000
-    ss, bufs, strs = {}, {}, {}
-    for model in (1, 2):
-        d = 2 if model == 1 else 3
-        ss[model] = SingleLevelSampler(model, pack, ids, tt, np.ones((len(ids), d)), variant="temp", seed=1, thinning=5,
-                                       burn_rows=K // 20, device=dev, co_resident_chains=len(ids))
-        bufs[model] = torch.empty((len(ids), K // 5, d + 1), dtype=torch.float64, device=dev)
-        strs[model] = torch.cuda.Stream(device=dev)
-
-    def both():
-        cur = torch.cuda.current_stream(dev)
-        for model in (1, 2):
-            strs[model].wait_stream(cur)
-            with torch.cuda.stream(strs[model]):
-                ss[model].run(K, samples=bufs[model])
-        for model in (1, 2):
-            cur.wait_stream(strs[model])
-    t4 = _timed(torch, both)
-    out["config4_ti_64_temperatures"] = {"chains": 2 * len(ids), "iters": K, "value": 2 * len(ids) * K / t4, "unit": UNIT,
-                                         "note": "models 1 and 2 on two streams, samples written"}
-    del ss, bufs
-    # config 5 share: 125 000 synthetic datasets x 4 chains = 500 000 chains, model 2, one thread per chain
-    concs, Y, _ = synthetic.generate(125000)
+    main_stream = torch.cuda.current_stream(dev)
+    w = {m: cx.wl[m]["flops_per_dataset"] for m in (1, 2)}
+    w0 = {m: np.array([flops_per_iteration(m, pack.groups[b:b + n], prior_only=True) for b, n in
+                       zip(pack.datasets["group_begin"], pack.datasets["n_groups"])], dtype=float) for m in (1, 2)}
+    for tag, temps in (("config4_ti_41_temperatures_reference_sweep", ti.temperature_ladder(40, 3)),
+                       ("config4_ti_64_temperatures", ti.temperature_ladder(63, 3))):
+        T = len(temps)
+        chains = 2 * 210 * T
+        iters = args.ti_iterations
+        # warm-up: the same call, short (brings up the NCCL communicator and the all-gather path, loads the kernels)
+        ti.run_ti(data, temps=temps, iterations=10000, segment=10000, seed=1, device=dev, pack=pack)
+        # rank-count independence: with a fixed lane count the result is bit-identical for every N (the digest)
+        chk = ti.run_ti(data, temps=temps, iterations=20000, segment=20000, seed=1, device=dev, pack=pack, lanes=2)
+        digest = hashlib.sha256(np.ascontiguousarray(chk["B12"]).tobytes()).hexdigest()[:16]
+        cx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(main_stream)
+        res = ti.run_ti(data, temps=temps, iterations=iters, segment=iters, seed=1, device=dev, pack=pack)
+        e1.record(main_stream)
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - t0
+        sec = cx.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+        sample_s = cx.max_over_ranks(res.get("sample_seconds", 0.0))
+        gather_s = cx.max_over_ranks(res["gather_seconds"])
+        lb = np.log(res["B12"])
+        flops = sum((w[m].sum() * (T - 1) + w0[m].sum()) for m in (1, 2)) / chains    # t = 0 chains: prior only
+        out[tag] = {"scaling": "strong", "chains": chains, "chains_per_gpu_rank0": res["chains_local"], "iters": iters,
+                    "value": chains * iters / sec, "unit": UNIT, "seconds": sec, "wall_seconds": cx.max_over_ranks(wall),
+                    "phase_seconds": {"sampling_max_over_ranks": sample_s, "all_gather_and_trapezium": gather_s},
+                    "lanes_rank0": res["lanes"], "flops_per_chain_iteration": float(flops),
+                    "ln_B12": {"mean_over_pairs": float(lb.mean()), "min": float(lb.min()), "max": float(lb.max()),
+                               "Amiodarone_hERG": float(lb[0])},
+                    "rank_count_independence": {"lanes": 2, "iterations": 20000, "B12_sha256_16": digest,
+                                                "note": "same digest at every N: sharding changes no bit"},
+                    "timing": "CUDA events on the launching stream around ti.run_ti (sampling on two streams ordered after "
+                              "it, NCCL all-gather of per-chain means, trapezium), barrier before, max over ranks",
+                    "reference": "python/PyHillTemp.py:151-161, python/compute_bayes_factors.py:77-100"}
+    # ---- config 5 ----
+    n_total = args.config5_datasets
+    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    t0 = time.perf_counter()
+    concs, Y, truth = synthetic.generate(hi - lo, offset=lo)
     sp = SinglePack.from_uniform(concs, Y)
+    t_pack = time.perf_counter() - t0
     ids5 = np.repeat(np.arange(sp.n_datasets, dtype=np.int32), 4)
     s5 = SingleLevelSampler(2, sp, ids5, 1.0, np.tile([6.0, 1.0, 6.0], (len(ids5), 1)), variant="fit", seed=9,
-                            thinning=5, device=dev)
-    K5 = 2000
-    buf5 = torch.empty((s5.n, K5 // 5, 4), dtype=torch.float64, device=dev)
-    t5 = _timed(torch, lambda: s5.run(K5, samples=buf5))
-    out["config5_synthetic_share"] = {"chains": s5.n, "iters": K5, "value": s5.n * K5 / t5, "unit": UNIT,
-                                      "lanes": s5.lanes, "note": "1/8 of 1M datasets x 4 chains (one GPU of eight)"}
+                            chain_id_base=4 * lo, thinning=5, device=dev)
+    K5 = args.config5_iters
+    buf5 = torch.empty((K5 // 5, s5.n, 4), dtype=torch.float64, device=dev)
+    s5.run(K5, samples=buf5, row_major=True)
+    cx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record(main_stream)
+    for _ in range(reps):
+        s5.run(K5, samples=buf5, row_major=True)
+    e1.record(main_stream)
+    torch.cuda.synchronize(dev)
+    sec5 = cx.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    pick = np.arange(0, sp.n_datasets, max(sp.n_datasets // 2000, 1))
+    w5 = float(np.mean([flops_per_iteration(2, sp.groups[b:b + n]) for b, n in
+                        zip(sp.datasets["group_begin"][pick], sp.datasets["n_groups"][pick])]))
+    out["config5_synthetic_1M_datasets"] = {
+        "scaling": "strong", "chains": 4 * n_total, "chains_per_gpu": s5.n, "iters": K5 * reps,
+        "value": 4.0 * n_total * K5 * reps / sec5, "unit": UNIT, "seconds": sec5, "lanes": s5.lanes,
+        "flops_per_chain_iteration": w5, "generate_and_pack_s_per_rank": round(t_pack, 2),
+        "note": "%d synthetic datasets x 4 chains, model 2, datasets sharded over the ranks (dataset k is the same for "
+                "every N), row-major samples written to HBM (%.1f GB per %d iterations per GPU); no collective"
+                % (n_total, buf5.numel() * 8 / 1e9, K5)}
     del buf5, s5
-    # config 3: hierarchical, every Crumb pair x 256 chains (grouped by number of experiments)
+    return out
+
+
+def config3(cx):
+    """Device-timed throughput of BASELINE config 3 (hierarchical; context, not the headline): four launches on four
+    streams, samples written, best of 3; the same through phf_am_hier_run_host."""
+    torch, dev = cx.torch, cx.dev
+    from _data import Table
+    from pyhillfit_b200.packing import HierPack
+    from pyhillfit_b200.sampler import HierarchicalSampler, hier_priors
+    out = {}
     table = Table("crumb_data")
     pr, shapes, scales, locs = hier_priors()
     pairs = table.pairs()
@@ -554,16 +695,23 @@ def other_configs(torch, dev, pack):
     for ip, (dg, ch) in enumerate(pairs):
         by_ne.setdefault(len(table.experiments(dg, ch)), []).append(ip)
     K3 = 1000
-    hier, tot_n = [], 0
+    hier, tot_n, tot_flops, forms = [], 0, 0.0, {}
     for ne, idxs in sorted(by_ne.items()):
-        hp = HierPack([table.experiments(*pairs[i]) for i in idxs])
+        exs = [table.experiments(*pairs[i]) for i in idxs]
+        hp = HierPack(exs)
         hid = np.repeat(np.arange(len(idxs), dtype=np.int32), 256)
         th0 = np.tile(np.concatenate(([1.0, 4.0, 6.0, 0.3], np.tile([5.5, 1.0], ne), [8.0])), (len(hid), 1))
         hs = HierarchicalSampler(hp, hid, th0, pr, seed=ne, thinning=5, device=dev)
         hb = torch.empty((hs.n, K3 // 5, hs.d + 1), dtype=torch.float64, device=dev)
         hier.append((hs, hb, torch.cuda.Stream(device=dev)))
         tot_n += hs.n
-    serial_t = sum(_timed(torch, lambda hs=hs, hb=hb: hs.run(K3, samples=hb)) for hs, hb, _ in hier)
+        tot_flops += 256.0 * sum(hier_flops_per_iteration(ne, sum(len(e) for e in ex)) for ex in exs)
+    per_ne = {}
+    serial_t = 0.0
+    for hs, hb, _ in hier:
+        t = _timed(torch, lambda hs=hs, hb=hb: hs.run(K3, samples=hb))
+        serial_t += t
+        per_ne["Ne=%d" % hs.n_expts] = {"chains": hs.n, "value_alone": hs.n * K3 / t}
 
     def all_at_once():   # the four launches are independent: one stream each, the small ones fill the big one's gaps
         ev = torch.cuda.Event()
@@ -616,76 +764,96 @@ def other_configs(torch, dev, pack):
                                           j["hs"].pack.datasets.nbytes for j in jobs)),
             "d2h_bytes_per_step": int(sum((j["samples"].numel() + j["state"].numel()) * 8 for j in jobs)),
             "api": "phf_am_hier_run_host (pinned host buffers, row-major samples, 8 overlapped segments/call, one host "
-                   "thread per number of experiments), best of 3"}
+                   "thread per number of experiments; the hierarchical loop keeps its burn-in rows: PyHillFit.py:514-515), "
+                   "best of 3"}
     del jobs
     out["config3_hierarchical"] = {"chains": tot_n, "iters": K3, "value": tot_n * K3 / tot_t, "unit": UNIT,
-                                   "value_back_to_back": tot_n * K3 / serial_t, "e2e": e2e3,
-                                   "note": "dim 11..17, four launches (Ne = 3, 4, 5, 6) on four streams; Ne = 3 (39 424 "
-                                           "chains) runs one thread per chain, the others one lane per parameter"}
+                                   "value_back_to_back": tot_n * K3 / serial_t, "e2e": e2e3, "per_n_expts": per_ne,
+                                   "flops_per_chain_iteration": tot_flops / tot_n,
+                                   "note": "dim 11..17, four launches (Ne = 3, 4, 5, 6) on four streams"}
     return out
 
 
-def run_e2e(args, torch, dev, pack, wl, samplers, rank, world, dist):
-    """Same step through phf_am_single_run_host: numpy/pinned host buffers in and out."""
+def run_e2e(cx, state0):
+    """The same metric through the reference-facing call, phf_am_single_run_host, with pinned HOST buffers.  One step =
+    one complete PyHillFit run of `--iters-per-step` iterations of every chain: start state and packed data copied in
+    (H2D), K iterations, the rows the reference SAVES copied back -- it drops the first quarter of the saved rows
+    before np.savetxt (python/PyHillFit.py:861-864), so those are neither written nor transferred
+    (cfg.discard_burn_rows) -- plus the final state (D2H).  The two models are driven by two host threads, each making
+    its `--e2e-steps` calls back to back (a call returns when its results are on the host), so one model's transfers
+    overlap the other's burn-in phase; the timed region is the wall clock from the barrier to the last call's return."""
     import ctypes as C
     from pyhillfit_b200 import _lib
+    args, torch, dev, pack, wl, rank, world = cx.args, cx.torch, cx.dev, cx.pack, cx.wl, cx.rank, cx.world
     L = _lib.load()
     thin, K = args.thinning, args.iters_per_step
-    rows = K // thin
+    saved = K // thin + 1
+    burn = saved // 4                       # burn_in_fraction = 4 (PyHillFit.py:37)
+    rows = saved - burn                     # rows burn .. saved-1 are kept
+    row_major = args.layout == "row"
     jobs = {}
     h2d = d2h = 0
     for model in (1, 2):
         w = wl[model]
         n, d = len(w["ids"]), w["d"]
-        st = torch.empty((n, _lib.state_size(d)), dtype=torch.float64).pin_memory()
-        st.copy_(samplers[model].state.cpu())
+        st0 = state0[model].pin_memory()
+        st = torch.empty_like(st0).pin_memory()
         # row-major samples: [row][chain][d+1], every segment is one contiguous device -> host transfer
-        smp = torch.empty((rows, n, d + 1) if args.e2e_layout == "row" else (n, rows, d + 1), dtype=torch.float64).pin_memory()
+        smp = torch.empty((rows, n, d + 1) if row_major else (n, rows, d + 1), dtype=torch.float64).pin_memory()
         ids = np.ascontiguousarray(w["ids"])
         temps = np.ones(n)
-        jobs[model] = dict(n=n, state=st, samples=smp, ids=ids, temps=temps, t0=samplers[model].t)
+        jobs[model] = dict(n=n, state0=st0, state=st, samples=smp, ids=ids, temps=temps)
         h2d += st.numel() * 8 + ids.nbytes + temps.nbytes + pack.datasets.nbytes + pack.groups.nbytes
         d2h += smp.numel() * 8 + st.numel() * 8
 
     def call(model):
         j = jobs[model]
-        cfg = _lib.AmConfig(model=model, reset_mean_at_adapt=0, t0=j["t0"], n_iters=K, thinning=thin,
-                            adapt_when=1000 * wl[model]["d"], burn_rows=0xFFFFFFFF, rows_capacity=rows, seed=25,
-                            chain_id_base=(rank * 2 + (model - 1)) * (1 << 32), stage_groups=samplers[model].stage_groups,
-                            block_threads=samplers[model].block_threads, lanes_per_chain=samplers[model].lanes,
-                            sample_layout=_lib.SAMPLES_ROW_MAJOR if args.e2e_layout == "row" else _lib.SAMPLES_CHAIN_MAJOR)
+        j["state"].copy_(j["state0"])       # a complete run starts from the start state (host copy, inside the timed region)
+        cfg = _lib.AmConfig(model=model, reset_mean_at_adapt=0, t0=0, n_iters=K, thinning=thin,
+                            adapt_when=1000 * wl[model]["d"], burn_rows=burn, discard_burn_rows=1, rows_capacity=rows,
+                            seed=25, chain_id_base=(rank * 2 + (model - 1)) * (1 << 32),
+                            stage_groups=cx.samplers[model].stage_groups, block_threads=cx.samplers[model].block_threads,
+                            lanes_per_chain=cx.samplers[model].lanes,
+                            sample_layout=_lib.SAMPLES_ROW_MAJOR if row_major else _lib.SAMPLES_CHAIN_MAJOR)
         rc = L.phf_am_single_run_host(C.byref(cfg), j["n"], j["state"].data_ptr(), j["ids"].ctypes.data,
                                       j["temps"].ctypes.data, pack.n_datasets, pack.datasets.ctypes.data,
                                       len(pack.groups), pack.groups.ctypes.data, j["samples"].data_ptr(),
                                       args.e2e_segments, dev.index)
         _lib.check(rc, "phf_am_single_run_host")
-        j["t0"] += K
 
-    def step():
-        th = [threading.Thread(target=call, args=(m,)) for m in (1, 2)]
+    def run(steps):
+        errs = []
+
+        def loop(model):
+            try:
+                for _ in range(steps):
+                    call(model)
+            except Exception as e:      # surface a failure of a worker thread
+                errs.append(e)
+        th = [threading.Thread(target=loop, args=(m,)) for m in (1, 2)]
         for t in th:
             t.start()
         for t in th:
             t.join()
+        if errs:
+            raise errs[0]
 
-    for _ in range(2):
-        step()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
+    run(2)
+    cx.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        step()
+    run(args.e2e_steps)
     torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+    dt = cx.max_over_ranks(time.perf_counter() - t0)
     total = float(sum(j["n"] for j in jobs.values())) * K * args.e2e_steps * world
+    finite = bool(all(np.isfinite(j["samples"][-1].numpy()).all() for j in jobs.values()))
     return {"value": total / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "steps": args.e2e_steps, "api": "phf_am_single_run_host (pinned host buffers, %s-major samples, %d overlapped segments/call)" % (args.e2e_layout, args.e2e_segments),
-            "timing": "host wall clock around synchronous calls (each call ends with a stream synchronise)"}
+            "steps": args.e2e_steps, "rows_kept_per_chain": rows, "rows_discarded_as_burn_in": burn - 1,
+            "last_row_finite": finite,
+            "api": "phf_am_single_run_host (pinned host buffers, %s-major samples, %d overlapped segments/call, "
+                   "cfg.discard_burn_rows = 1: the burn-in rows PyHillFit.py:861-864 drops are not transferred; one host "
+                   "thread per model, calls back to back)" % (args.layout, args.e2e_segments),
+            "timing": "host wall clock from the barrier to the return of the last call (each call ends with a stream "
+                      "synchronise); max over ranks"}
 
 
 if __name__ == "__main__":

@@ -118,11 +118,21 @@ typedef struct phf_am_config {
     int32_t cta_order;           /* single-level only.  0: chain blocks are run in order of decreasing cost (censored
                                     doses per dataset), which balances the SMs when the datasets differ; 1: in index
                                     order.  Results do not depend on it. */
+    int32_t discard_burn_rows;   /* 1: saved rows with index < burn_rows are neither written to `samples` nor (host
+                                    entry points) copied back -- the rows python/PyHillFit.py:861-864 and
+                                    python/PyHillTemp.py:125 drop before saving.  `samples` then starts at row
+                                    max(burn_rows, first row of this call).  0: every saved row is written (the
+                                    hierarchical loop keeps its burn-in: python/PyHillFit.py:514-515). */
+    int32_t reserved;            /* must be 0 */
 } phf_am_config;
 #define PHF_SAMPLES_CHAIN_MAJOR 0
 #define PHF_SAMPLES_ROW_MAJOR 1
 
-/* Evaluate the target at theta0 and fill `state` (mean = theta0, cov = cov0, loga = 0, counters = 0). */
+/* Evaluate the target at theta0 and fill `state` (mean = theta0, cov = cov0, loga = 0, counters = 0).  A diagonal
+ * entry of cov0 that is not positive (a theta0 component of exactly 0 under Sigma0 = 0.05 diag|theta0|,
+ * python/PyHillFit.py:751) is stored as PHF_COV0_DIAG_FLOOR: that coordinate then stays where it is -- what the
+ * reference's SVD-based multivariate_normal does with a zero variance -- instead of poisoning the Cholesky factor. */
+#define PHF_COV0_DIAG_FLOOR 1e-60
 int phf_am_single_init(int model, int64_t n_chains, const double *theta0 /* [n,d] */,
                        const double *cov0_tri /* [n, d(d+1)/2] */, const int32_t *dataset_id,
                        const double *temperature, const phf_dataset *datasets, const phf_dose_group *groups,
@@ -139,7 +149,8 @@ int phf_am_single_resident_ctas(int model, int lanes, int block_threads, int64_t
 /*
  * Run cfg->n_iters iterations of every chain.  `samples` ([n_chains, rows_capacity, d+1], or
  * [rows_capacity, n_chains, d+1] with cfg->sample_layout = PHF_SAMPLES_ROW_MAJOR; may be NULL)
- * receives (theta, log_target) for each saved row of this call: local row = t/thinning - t0/thinning - 1.
+ * receives (theta, log_target) for each saved row of this call: local row = t/thinning - t0/thinning - 1
+ * (with cfg->discard_burn_rows: t/thinning - max(burn_rows, t0/thinning + 1)).
  * Chains must be sorted by dataset_id when cfg->stage_groups > 0 (a CTA of B threads covers B / lanes chains).
  */
 int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, double *state, const int32_t *dataset_id,
@@ -182,7 +193,11 @@ int phf_hier_log_target_batch(int64_t n, const double *theta, int32_t theta_stri
  * kernel for tens of thousands of chains; cfg->lanes_per_chain = 0 picks it for n_expts <= 3 and >= 80 chains per
  * SM); up to PHF_HIER_BIG_MAX_EXPTS: warp-per-chain kernel (takes a stream-ordered temporary of
  * n_chains * dim (dim+1) / 2 doubles for the Cholesky factors).  The kernels run the same algorithm on the same
- * Philox stream and agree to rounding (the log-target's summation order differs). */
+ * Philox stream and agree to rounding (the log-target's summation order differs).
+ * phf_am_hier_init also VALIDATES the packed data the run calls will trust: every chain's dataset must have exactly
+ * n_expts experiments and every point of it an experiment index in [0, n_expts) (the kernels use that index as a
+ * shuffle lane / shared-memory index); otherwise PHF_EINVAL.  The check reads a flag back, so init synchronises
+ * `stream`; phf_am_hier_run is asynchronous and trusts a pack that init accepted. */
 int phf_am_hier_init(int32_t n_expts, int64_t n_chains, const double *theta0 /* [n,dim] */,
                      const double *cov0_tri /* [n, dim(dim+1)/2] */, const int32_t *dataset_id,
                      const phf_hier_dataset *datasets, const phf_hier_point *points,
@@ -218,6 +233,13 @@ int phf_am_single_run_host(const phf_am_config *cfg, int64_t n_chains, double *s
                            const double *temperature, int32_t n_datasets, const phf_dataset *datasets,
                            int32_t n_groups, const phf_dose_group *groups, double *samples, int32_t n_segments,
                            int32_t device);
+
+/* Thread safety of the *_host entry points: each call locks the workspace (device buffers, two streams, events) of its
+ * (device, model) or (device, n_expts) pair for its whole duration, so calls for different pairs run concurrently
+ * (bench.py drives models 1 and 2 from two host threads) and calls for the same pair serialise.
+ * phf_release_workspaces() frees every workspace of every device (buffers, streams, events); later calls re-create
+ * what they need.  Returns PHF_OK or the first CUDA error. */
+int phf_release_workspaces(void);
 
 /* The same for the hierarchical sampler (python/PyHillFit.py:431-511 with numpy arrays in and out): all chains of
  * a call share n_expts; `priors` is a HOST pointer as everywhere. */

@@ -108,7 +108,10 @@ def make_state(theta0, lt, ll1, cov0):
     s[d] = lt
     s[d + 1] = ll1
     s[d + 2:2 * d + 2] = theta0
-    s[2 * d + 2:2 * d + 2 + d * d] = np.asarray(cov0).reshape(-1)
+    cov = np.array(cov0, dtype=np.float64).reshape(d, d)
+    dg = np.diag(cov).copy()
+    cov[np.diag_indices(d)] = np.where(dg > 0, dg, 1e-60)   # PHF_COV0_DIAG_FLOOR (hill_oracle.COV0_DIAG_FLOOR)
+    s[2 * d + 2:2 * d + 2 + d * d] = cov.reshape(-1)
     return s
 
 

@@ -278,6 +278,11 @@ def philox_draw(seed, chain, t, d):
 # SURVEY.md section 3.5 tabulates the differences.
 # ----------------------------------------------------------------------------
 PIVOT_FLOOR = 1e-12
+# A zero variance in Sigma0 (a theta0 component of exactly 0 under 0.05 diag|theta0|) freezes that coordinate in the
+# reference (numpy's SVD-based multivariate_normal draws it with zero spread).  The Cholesky-based Philox path stores
+# such a diagonal entry as COV0_DIAG_FLOOR instead (include/pyhillfit_b200.h: PHF_COV0_DIAG_FLOOR): the coordinate
+# moves by ~1e-30, i.e. stays where it is, and the factor stays finite.
+COV0_DIAG_FLOOR = 1e-60
 
 
 def guarded_cholesky(a):
@@ -324,6 +329,9 @@ def adaptive_metropolis(target, theta0, iterations, thinning, variant, rng="nump
     theta_cur = np.array(theta0, dtype=float)
     d = len(theta_cur)
     cov, adapt_when, reset_mean = am_defaults(variant, theta_cur)
+    if rng == "philox":
+        dg = np.diag(cov).copy()
+        cov[np.diag_indices(d)] = np.where(dg > 0, dg, COV0_DIAG_FLOOR)
     mean = np.copy(theta_cur)
     log_target_cur = target(theta_cur)
     num_saved = iterations // thinning + 1

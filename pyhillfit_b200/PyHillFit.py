@@ -97,25 +97,33 @@ def run_single_level(dr, args, pairs):
         theta0 = theta0 * jit
     saved_iterations = args.iterations // args.thinning + 1
     burn = saved_iterations // args.burn_in_fraction
-    s = SingleLevelSampler(args.model, pack, ids, 1.0, theta0, variant="fit", seed=args.seed, thinning=args.thinning,
-                           burn_rows=burn)
+    # (-m 1 and -m 2 are separate invocations with the same --seed: the model goes into the Philox chain id, as in
+    # pyhillfit_b200/ti.py, so that the two models' chains do not share their draws)
+    s = SingleLevelSampler(args.model, pack, ids, 1.0, theta0, variant="fit", seed=args.seed,
+                           chain_id_base=(args.model - 1) * (1 << 40), thinning=args.thinning, burn_rows=burn)
     d = s.d
-    chain = torch.empty((s.n, saved_iterations, d + 1), dtype=torch.float64, device=s.device)
-    chain[:, 0, :] = s.initial_row()
+    # only the rows the reference saves (chain[burn:], PyHillFit.py:861-864) are written by the kernel and copied back
+    kept = saved_iterations - burn
+    chain = torch.empty((s.n, kept, d + 1), dtype=torch.float64, device=s.device)
+    at = 0
+    if burn == 0:
+        chain[:, 0, :] = s.initial_row()
+        at = 1
     torch.cuda.synchronize()
     print("packing, CUDA start-up, sampler state: {:.2f} s".format(time.time() - t_phase))
     start = time.time()
     done = 0
     while done < args.iterations:
         k = min(args.segment - args.segment % args.thinning or args.thinning, args.iterations - done)
-        r0 = done // args.thinning + 1
-        seg = s.run(k)
-        chain[:, r0:r0 + seg.shape[1], :] = seg
+        seg = s.run(k, discard_burn=True)
+        chain[:, at:at + seg.shape[1], :] = seg
+        at += seg.shape[1]
         done += k
     torch.cuda.synchronize()
+    assert at == kept
     print("\n{} chains x {} iterations in {:.2f} s on the GPU\n".format(s.n, args.iterations, time.time() - start))
     t_phase = time.time()
-    host = chain[:, burn:, :].cpu().numpy()                 # remove burn-in before saving (PyHillFit.py:861-864)
+    host = chain.cpu().numpy()                              # burn-in already removed (PyHillFit.py:861-864)
     print("chains to the host: {:.2f} s".format(time.time() - t_phase))
     t_phase = time.time()
     for j, job in enumerate(jobs):

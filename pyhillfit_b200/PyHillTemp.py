@@ -49,19 +49,28 @@ def do_mcmc_all_temperatures(dr, args, concs, responses, temperatures):
     burn = num_saved // args.burn_in_fraction
     pack = SinglePack([(concs, responses)])
     tt = np.repeat(np.asarray(temperatures, dtype=np.float64), R)
+    # models 1 and 2 are run by separate invocations with the same --seed: the model goes into the Philox chain id
+    # (as pyhillfit_b200/ti.py does) so that chain k of model 1 and chain k of model 2 do not share their draws
     s = SingleLevelSampler(args.model, pack, np.zeros(T * R, dtype=np.int32), tt, np.ones((T * R, d)), variant="temp",
-                           seed=args.seed, thinning=args.thinning, burn_rows=burn)
-    chain = torch.empty((s.n, num_saved, d + 1), dtype=torch.float64, device=s.device)
-    chain[:, 0, :] = s.initial_row()
+                           seed=args.seed, chain_id_base=(args.model - 1) * (1 << 40), thinning=args.thinning,
+                           burn_rows=burn)
+    # only the rows the reference keeps (chain[burn:], PyHillTemp.py:125) are written by the kernel and copied back
+    kept = num_saved - max(burn, 0)
+    chain = torch.empty((s.n, kept, d + 1), dtype=torch.float64, device=s.device)
+    at = 0
+    if burn == 0:
+        chain[:, 0, :] = s.initial_row()
+        at = 1
     done = 0
     while done < args.iterations:
         k = min(args.segment - args.segment % args.thinning or args.thinning, args.iterations - done)
-        r0 = done // args.thinning + 1
-        seg = s.run(k)
-        chain[:, r0:r0 + seg.shape[1], :] = seg
+        seg = s.run(k, discard_burn=True)
+        chain[:, at:at + seg.shape[1], :] = seg
+        at += seg.shape[1]
         done += k
     torch.cuda.synchronize()
-    host = chain[:, burn:, :].cpu().numpy().reshape(T, R, num_saved - burn, d + 1)
+    assert at == kept
+    host = chain.cpu().numpy().reshape(T, R, kept, d + 1)
     return host, s.loglik_t1_mean().reshape(T, R)
 
 

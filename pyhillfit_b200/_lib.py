@@ -24,7 +24,7 @@ class AmConfig(C.Structure):
                 ("burn_rows", C.c_uint32), ("rows_capacity", C.c_uint32), ("seed", C.c_uint64),
                 ("chain_id_base", C.c_uint64), ("stage_groups", C.c_int32), ("block_threads", C.c_int32),
                 ("lanes_per_chain", C.c_int32), ("min_ctas_hint", C.c_int32), ("sample_layout", C.c_int32),
-                ("cta_order", C.c_int32)]
+                ("cta_order", C.c_int32), ("discard_burn_rows", C.c_int32), ("reserved", C.c_int32)]
 
 
 SAMPLES_CHAIN_MAJOR, SAMPLES_ROW_MAJOR = 0, 1
@@ -49,6 +49,7 @@ assert HIER_POINT_DTYPE.itemsize == 32 and HIER_DATASET_DTYPE.itemsize == 16
 EXPORTS = ["phf_log_target_batch", "phf_am_single_init", "phf_am_single_run", "phf_am_single_lanes",
            "phf_am_single_resident_ctas", "phf_hier_log_target_batch",
            "phf_am_hier_init", "phf_am_hier_run", "phf_am_single_run_host", "phf_am_hier_run_host",
+           "phf_release_workspaces",
            "phf_write_rows_text_host",
            "phf_hier_predictive_cdfs", "phf_format_e18", "phf_format_e18_mismatches", "phf_version", "phf_last_error",
            "phf_fp64_peak_probe", "phf_launch_count"]

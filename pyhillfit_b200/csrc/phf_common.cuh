@@ -25,4 +25,18 @@ inline int default_block_threads(int64_t n_threads)
     return 128;
 }
 
+// First saved row a call writes to `samples` (row index = t / thinning) and the number it writes: every saved row of
+// the call, or with cfg.discard_burn_rows only those with index >= burn_rows (python/PyHillFit.py:861-864,
+// python/PyHillTemp.py:125 drop the others before saving).
+__host__ __device__ inline uint32_t first_row_written(const phf_am_config &c)
+{
+    const uint32_t first = c.t0 / c.thinning + 1;
+    return (c.discard_burn_rows && c.burn_rows != 0xFFFFFFFFu && c.burn_rows > first) ? c.burn_rows : first;
+}
+__host__ __device__ inline uint32_t rows_written(const phf_am_config &c)
+{
+    const uint32_t last = (c.t0 + c.n_iters) / c.thinning, from = first_row_written(c);
+    return last >= from ? last - from + 1 : 0;
+}
+
 }  // namespace phf

@@ -167,6 +167,57 @@ __global__ void __launch_bounds__(128) hier_log_target_batch_kernel(int64_t n, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// validation of a packed hierarchical data set (phf_am_hier_init, phf_hier_log_target_batch): the sampler kernels use
+// points[].expt as a shuffle source lane / shared-memory index and take the dimension from the launch, so a pack that
+// disagrees with the launch would read out of range silently.  One thread per chain; flag bit 0: a chain's dataset
+// does not have the launch's number of experiments (or does not fit the theta stride), bit 1: a point's experiment
+// index is outside [0, n_expts), bit 2: negative point range.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) hier_validate_kernel(int64_t n, int32_t n_expts, int32_t theta_stride,
+                                                            const int32_t *__restrict__ dataset_id,
+                                                            const phf_hier_dataset *__restrict__ datasets,
+                                                            const phf_hier_point *__restrict__ points,
+                                                            int *__restrict__ flag)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const phf_hier_dataset ds = datasets[dataset_id[i]];
+    int bad = 0;
+    if (n_expts > 0 && ds.n_expts != n_expts) bad |= 1;
+    if (ds.n_expts < 1 || ds.n_expts > PHF_HIER_BIG_MAX_EXPTS) bad |= 1;
+    if (theta_stride > 0 && (5 + 2 * ds.n_expts > theta_stride || (theta_stride <= 31 && ds.n_expts > PHF_HIER_MAX_EXPTS)))
+        bad |= 1;
+    if (ds.point_begin < 0 || ds.n_points < 0) bad |= 4;
+    if (!bad)
+        for (int p = 0; p < ds.n_points; ++p) {
+            const int e = points[ds.point_begin + p].expt;
+            if (e < 0 || e >= ds.n_expts) bad |= 2;
+        }
+    if (bad) atomicOr(flag, bad);
+}
+
+static int validate_hier_pack(int64_t n, int32_t n_expts, int32_t theta_stride, const int32_t *dataset_id,
+                              const phf_hier_dataset *datasets, const phf_hier_point *points, cudaStream_t s,
+                              const char *who)
+{
+    int *d_flag = nullptr, h_flag = 0;
+    cudaError_t e;
+    if ((e = cudaMallocAsync(&d_flag, sizeof(int), s))) return set_cuda_error(e, "cudaMallocAsync");
+    if ((e = cudaMemsetAsync(d_flag, 0, sizeof(int), s))) return set_cuda_error(e, "cudaMemsetAsync");
+    hier_validate_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(n, n_expts, theta_stride, dataset_id, datasets, points,
+                                                                     d_flag);
+    count_launch();
+    if (int rc = check_launch("hier_validate_kernel")) return rc;
+    if ((e = cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s)) || (e = cudaFreeAsync(d_flag, s)) ||
+        (e = cudaStreamSynchronize(s)))
+        return set_cuda_error(e, who);
+    if (h_flag & 1) return set_error(PHF_EINVAL, "hierarchical pack: a chain's dataset does not have the launch's number of experiments / does not fit theta_stride");
+    if (h_flag & 2) return set_error(PHF_EINVAL, "hierarchical pack: a point's experiment index is outside [0, n_expts)");
+    if (h_flag & 4) return set_error(PHF_EINVAL, "hierarchical pack: negative point range");
+    return PHF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // state init
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) am_hier_init_kernel(int32_t dim, int64_t n, const double *__restrict__ theta0,
@@ -194,6 +245,13 @@ __global__ void __launch_bounds__(128) am_hier_init_kernel(int32_t dim, int64_t 
         s[dim + 2 + gl] = th_j;
     }
     for (int k = gl; k < nt; k += G) s[2 * dim + 2 + k] = cov0[i * nt + k];
+    __syncwarp();
+    // a non-positive diagonal entry of cov0 becomes PHF_COV0_DIAG_FLOOR (include/pyhillfit_b200.h)
+    if (gl < dim) {
+        const int q = gl * (gl + 1) / 2 + gl;
+        const double v = cov0[i * nt + q];
+        if (!(v > 0.0) && v == v) s[2 * dim + 2 + q] = PHF_COV0_DIAG_FLOOR;
+    }
     if (gl == 0) {
         s[dim] = lt;
         s[dim + 1] = 0.0;
@@ -260,7 +318,7 @@ __global__ void __launch_bounds__(128, hier_min_ctas(DIM)) am_hier_kernel(phf_am
     uint32_t t = cfg.t0;
     uint32_t until_save = cfg.thinning - (t % cfg.thinning);
     uint32_t row = t / cfg.thinning;
-    const uint32_t row_base = row + 1;
+    const uint32_t row_base = first_row_written(cfg);
     // chain-major: rows of a chain DIM+1 doubles apart; row-major: n chains apart (phf_am_config.sample_layout)
     const bool row_major = cfg.sample_layout == PHF_SAMPLES_ROW_MAJOR;
     double *out = samples ? samples + (row_major ? (size_t)c : (size_t)c * cfg.rows_capacity) * (DIM + 1) : nullptr;
@@ -338,7 +396,7 @@ __global__ void __launch_bounds__(128, hier_min_ctas(DIM)) am_hier_kernel(phf_am
         if (--until_save == 0u) {
             until_save = cfg.thinning;
             ++row;
-            if (out && active) {
+            if (out && active && row >= row_base) {
                 double *o = out + (size_t)(row - row_base) * row_stride;
                 if (row_ok) o[gl] = th_j;
                 if (gl == DIM) o[DIM] = lt;
@@ -408,6 +466,9 @@ extern "C" int phf_hier_log_target_batch(int64_t n, const double *theta, int32_t
         return set_error(PHF_EINVAL, "phf_hier_log_target_batch: null pointer");
     if (theta_stride < 7) return set_error(PHF_EINVAL, "theta_stride < 7");
     if (n == 0) return PHF_OK;
+    if (int rc = validate_hier_pack(n, 0, theta_stride, dataset_id, datasets, points, (cudaStream_t)stream,
+                                    "phf_hier_log_target_batch"))
+        return rc;
     if (theta_stride > 31) {
         if (theta_stride > 5 + 2 * PHF_HIER_BIG_MAX_EXPTS + 64) return set_error(PHF_ENOTSUP, "theta_stride too large");
         return hier_big_target_launch(n, theta, theta_stride, nullptr, dataset_id, datasets, points, *priors, log_target,
@@ -431,6 +492,9 @@ extern "C" int phf_am_hier_init(int32_t n_expts, int64_t n_chains, const double 
         (n_chains > 0 && (!theta0 || !cov0_tri || !dataset_id || !datasets || !points || !state)))
         return set_error(PHF_EINVAL, "phf_am_hier_init: null pointer");
     if (n_chains == 0) return PHF_OK;
+    if (int rc = validate_hier_pack(n_chains, n_expts, 0, dataset_id, datasets, points, (cudaStream_t)stream,
+                                    "phf_am_hier_init"))
+        return rc;
     if (n_expts > PHF_HIER_MAX_EXPTS)
         return hier_big_target_launch(n_chains, theta0, 5 + 2 * n_expts, cov0_tri, dataset_id, datasets, points, *priors,
                                       nullptr, state, (cudaStream_t)stream);
@@ -455,8 +519,7 @@ extern "C" int phf_am_hier_run(const phf_am_config *cfg, int32_t n_expts, int64_
     if (n_chains < 0 || (n_chains > 0 && (!state || !dataset_id || !datasets || !points)))
         return set_error(PHF_EINVAL, "phf_am_hier_run: null pointer");
     if ((uint64_t)cfg->t0 + cfg->n_iters > 0xFFFFFFFFull) return set_error(PHF_EINVAL, "iteration counter overflow");
-    const uint32_t rows = (cfg->t0 + cfg->n_iters) / cfg->thinning - cfg->t0 / cfg->thinning;
-    if (samples && rows > cfg->rows_capacity)
+    if (samples && rows_written(*cfg) > cfg->rows_capacity)
         return set_error(PHF_EINVAL, "cfg.rows_capacity is smaller than the rows this call produces");
     if (n_chains == 0 || cfg->n_iters == 0) return PHF_OK;
     cudaStream_t s = (cudaStream_t)stream;

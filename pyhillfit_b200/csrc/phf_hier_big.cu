@@ -131,6 +131,11 @@ __global__ void __launch_bounds__(32) hier_big_target_kernel(int64_t n, const do
             s[dim + 2 + j] = th[j];
         }
         for (int k = lane; k < nt; k += 32) s[2 * dim + 2 + k] = cov0[i * (size_t)nt + k];
+        __syncwarp();
+        for (int j = lane; j < dim; j += 32) {  // non-positive diagonal of cov0 -> PHF_COV0_DIAG_FLOOR (see the header)
+            const double v = cov0[i * (size_t)nt + rm(j, j)];
+            if (!(v > 0.0) && v == v) s[2 * dim + 2 + rm(j, j)] = PHF_COV0_DIAG_FLOOR;
+        }
         if (lane == 0) {
             s[dim] = lt;
             s[dim + 1] = 0.0;
@@ -177,7 +182,7 @@ __global__ void __launch_bounds__(32) am_hier_big_kernel(phf_am_config cfg, int3
     uint32_t t = cfg.t0;
     uint32_t until_save = cfg.thinning - (t % cfg.thinning);
     uint32_t row = t / cfg.thinning;
-    const uint32_t row_base = row + 1;
+    const uint32_t row_base = first_row_written(cfg);
     const bool row_major = cfg.sample_layout == PHF_SAMPLES_ROW_MAJOR;  // phf_am_config.sample_layout
     double *out = samples ? samples + (row_major ? (size_t)c : (size_t)c * cfg.rows_capacity) * (dim + 1) : nullptr;
     const size_t row_stride = row_major ? (size_t)n * (dim + 1) : (size_t)(dim + 1);
@@ -271,7 +276,7 @@ __global__ void __launch_bounds__(32) am_hier_big_kernel(phf_am_config cfg, int3
         if (--until_save == 0u) {
             until_save = cfg.thinning;
             ++row;
-            if (out) {
+            if (out && row >= row_base) {
                 double *o = out + (size_t)(row - row_base) * row_stride;
                 for (int j = lane; j < dim; j += 32) o[j] = th[j];
                 if (lane == 0) o[dim] = lt;

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(32 * HierThreadCfg<NE>::kMaxWarps) __maxnreg__
     uint32_t t = cfg.t0;
     uint32_t until_save = cfg.thinning - (t % cfg.thinning);
     uint32_t row = t / cfg.thinning;
-    const uint32_t row_base = row + 1;
+    const uint32_t row_base = first_row_written(cfg);
     // chain-major: rows of a chain DIM+1 doubles apart; row-major: n chains apart (phf_am_config.sample_layout)
     const bool row_major = cfg.sample_layout == PHF_SAMPLES_ROW_MAJOR;
     double *out = samples ? samples + (row_major ? (size_t)c : (size_t)c * cfg.rows_capacity) * (DIM + 1) : nullptr;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(32 * HierThreadCfg<NE>::kMaxWarps) __maxnreg__
         if (--until_save == 0u) {
             until_save = cfg.thinning;
             ++row;
-            if (out && active) {
+            if (out && active && row >= row_base) {
                 double *o = out + (size_t)(row - row_base) * row_stride;
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) o[k] = th[k];

@@ -98,7 +98,8 @@ PHF_DI Philox4 philox_call(uint64_t seed, uint64_t chain, uint32_t t, uint32_t j
     return philox4x32_10(t, j, (uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
-// 53-bit uniform in (0,1): replaces npr.rand() (PyHillFit.py:487,834; PyHillTemp.py:100)
+// 53-bit uniform (v + 1/2) 2^-53 in (0, 1] -- v = 2^53 - 1 rounds to exactly 1.0, whose log is 0: the proposal is then
+// accepted iff lt* > lt, a measure-zero difference from npr.rand()'s [0,1) (PyHillFit.py:487,834; PyHillTemp.py:100)
 PHF_DI double uniform53(uint32_t w0, uint32_t w1)
 {
     const unsigned long long v = (((unsigned long long)w0 << 32) | w1) >> 11;

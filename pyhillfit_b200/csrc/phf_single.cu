@@ -62,8 +62,16 @@ __global__ void __launch_bounds__(128) am_single_init_kernel(int64_t n, const do
     }
     s[D] = lt;
     s[D + 1] = l1;
+    {   // a non-positive diagonal entry of cov0 becomes PHF_COV0_DIAG_FLOOR (include/pyhillfit_b200.h)
+        int q = 0;
 #pragma unroll
-    for (int k = 0; k < NT; ++k) s[2 * D + 2 + k] = cov0[i * NT + k];
+        for (int r = 0; r < D; ++r)
+#pragma unroll
+            for (int c2 = 0; c2 <= r; ++c2, ++q) {
+                const double v = cov0[i * NT + q];
+                s[2 * D + 2 + q] = (r == c2 && !(v > 0.0) && v == v) ? PHF_COV0_DIAG_FLOOR : v;
+            }
+    }
     s[2 * D + 2 + NT] = 0.0;      // loga
     s[2 * D + 2 + NT + 1] = 0.0;  // loglik_t1_sum
     s[2 * D + 2 + NT + 2] = 0.0;  // n_accepted
@@ -190,7 +198,7 @@ PHF_DI void am_step(const double *T, const ChainConst &cc, ChainRegs<MODEL> &s, 
     if (--until_save == 0u) {
         until_save = cc.thinning;
         ++row;
-        if (cc.out && cc.active) {
+        if (cc.out && cc.active && row >= cc.row_base) {
             double *o = cc.out + (size_t)(row - cc.row_base) * cc.row_stride;
             // the G lanes of the chain write the row's D+1 columns between them
 #pragma unroll
@@ -340,7 +348,7 @@ __global__ void __launch_bounds__(128, MINB)
     uint32_t t = cfg.t0;
     uint32_t until_save = cfg.thinning - (t % cfg.thinning);
     uint32_t row = t / cfg.thinning;
-    cc.row_base = row + 1;
+    cc.row_base = first_row_written(cfg);  // (rows below it -- discarded burn-in -- are not written)
     // chain-major: rows of a chain D+1 doubles apart; row-major: n chains apart (phf_am_config.sample_layout)
     const bool row_major = cfg.sample_layout == PHF_SAMPLES_ROW_MAJOR;
     cc.out = samples ? samples + (row_major ? (size_t)c : (size_t)c * cfg.rows_capacity) * (D + 1) : nullptr;
@@ -507,8 +515,7 @@ extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, dou
     if (n_chains < 0 || (n_chains > 0 && (!state || !dataset_id || !temperature || !datasets || !groups)))
         return set_error(PHF_EINVAL, "phf_am_single_run: null pointer");
     if ((uint64_t)cfg->t0 + cfg->n_iters > 0xFFFFFFFFull) return set_error(PHF_EINVAL, "iteration counter overflow");
-    const uint32_t rows = (cfg->t0 + cfg->n_iters) / cfg->thinning - cfg->t0 / cfg->thinning;
-    if (samples && rows > cfg->rows_capacity)
+    if (samples && rows_written(*cfg) > cfg->rows_capacity)
         return set_error(PHF_EINVAL, "cfg.rows_capacity is smaller than the rows this call produces");
     if (n_chains == 0 || cfg->n_iters == 0) return PHF_OK;
 

@@ -44,3 +44,14 @@ def ess_min(chain):
 def mcse_mean(x):
     x = np.asarray(x, dtype=np.float64)
     return float(x.std(ddof=1) / np.sqrt(ess_geyer(x)))
+
+
+def ess_quantile_indicator(x, q):
+    """ESS of the indicator series 1[x_t <= q]: Var(F_hat(q)) = p (1 - p) / ESS, p = F(q) -- the effective sample size
+    that governs the Monte-Carlo error of a quantile estimate (a tail indicator mixes more slowly than the mean)."""
+    return ess_geyer((np.asarray(x, dtype=np.float64) <= q).astype(np.float64))
+
+
+def quantile_mcse(p, ess_p, density):
+    """Monte-Carlo standard error of the p-quantile estimate: sqrt(p (1 - p) / ESS_p) / f(q_p)."""
+    return np.sqrt(p * (1.0 - p) / ess_p) / density

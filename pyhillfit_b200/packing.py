@@ -163,6 +163,17 @@ class SinglePack:
             self._dev[key] = (d, g)
         return self._dev[key]
 
+    def dataset_cost(self, model=2):
+        """Relative cost of one adaptive-Metropolis iteration per dataset (SURVEY.md section 8d's cost table: a Hill
+        curve per unique dose, an erfcx + log per censored dose, plus the fixed proposal / accept / adapt work) --
+        the weight ranks are balanced by when a chain list is sharded (dist.shard_bounds)."""
+        gb, ng = self.datasets["group_begin"].astype(np.int64), self.datasets["n_groups"].astype(np.int64)
+        cens = ((self.groups["n0"] > 0).astype(np.float64) + (self.groups["n100"] > 0)).cumsum()
+        cens = np.concatenate(([0.0], cens))
+        n_cens = cens[gb + ng] - cens[gb]
+        fixed = 560.0 if model == 2 else 470.0
+        return fixed + 58.0 * ng + 133.0 * n_cens
+
     def stage_groups_needed(self, dataset_id, block_threads):
         """max over CTAs of the contiguous dose-group range they touch (chains sorted by dataset)."""
         ids = np.asarray(dataset_id)

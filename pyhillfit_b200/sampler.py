@@ -72,11 +72,15 @@ class _Base:
     def acceptance(self):
         return self.state_fields()["n_accepted"] / max(self.t, 1)
 
-    def rows_for(self, n_iters):
-        return (self.t + n_iters) // self.thinning - self.t // self.thinning
+    def rows_for(self, n_iters, discard_burn=False):
+        """rows a run of n_iters writes: every saved row, or with discard_burn only those with index >= burn_rows"""
+        first, last = self.t // self.thinning + 1, (self.t + n_iters) // self.thinning
+        if discard_burn and self.burn_rows != NO_BURN:
+            first = max(first, int(self.burn_rows))
+        return max(last - first + 1, 0)
 
-    def _config(self, n_iters, rows_capacity, row_major=False):
-        return _lib.AmConfig(sample_layout=_lib.SAMPLES_ROW_MAJOR if row_major else _lib.SAMPLES_CHAIN_MAJOR,
+    def _config(self, n_iters, rows_capacity, row_major=False, discard_burn=False):
+        return _lib.AmConfig(discard_burn_rows=int(bool(discard_burn)), sample_layout=_lib.SAMPLES_ROW_MAJOR if row_major else _lib.SAMPLES_CHAIN_MAJOR,
                              model=getattr(self, "model", 0), reset_mean_at_adapt=int(self.reset_mean), t0=self.t,
                              n_iters=int(n_iters), thinning=self.thinning, adapt_when=int(self.adapt_when),
                              burn_rows=int(self.burn_rows), rows_capacity=int(rows_capacity), seed=int(self.seed),
@@ -161,13 +165,14 @@ class SingleLevelSampler(_Base):
         """[n, d+1] row 0 of every chain: (theta0, log_target(theta0)) -- call before run()."""
         return self.state[:, :self.d + 1].clone()
 
-    def run(self, n_iters, samples=None, keep=True, row_major=False):
+    def run(self, n_iters, samples=None, keep=True, row_major=False, discard_burn=False):
         """Advance every chain by n_iters.  Returns the device tensor of rows saved by this call (a view of `samples`
         if given): [n, rows, d+1], or [rows, n, d+1] with row_major=True (one saved iteration of all chains
         contiguous: coalesced write-out, contiguous transfers); None when keep=False (thermodynamic-integration-only
-        runs)."""
+        runs).  discard_burn=True: rows with index < burn_rows are not written at all (what PyHillFit.py:861-864 and
+        PyHillTemp.py:125 drop before saving); the returned rows start at max(burn_rows, first row of this call)."""
         torch = self.torch
-        rows = self.rows_for(n_iters)
+        rows = self.rows_for(n_iters, discard_burn)
         cap = rows
         ax_n, ax_r = (1, 0) if row_major else (0, 1)
         if keep:
@@ -176,7 +181,7 @@ class SingleLevelSampler(_Base):
                 samples = torch.empty(shape, dtype=torch.float64, device=self.device)
             cap = samples.shape[ax_r]
             assert samples.shape[ax_n] == self.n and samples.shape[2] == self.d + 1 and samples.is_contiguous()
-        cfg = self._config(n_iters, cap, row_major)
+        cfg = self._config(n_iters, cap, row_major, discard_burn)
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().phf_am_single_run(C.byref(cfg), self.n, self.state.data_ptr(),
                                                      self.dataset_id.data_ptr(), self.temperature.data_ptr(),

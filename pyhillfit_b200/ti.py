@@ -38,26 +38,29 @@ def log_py_from_means(temps, means):
 
 
 def run_ti(datasets, models=(1, 2), temps=None, replicates=1, iterations=500000, thinning=5, burn_in_fraction=4,
-           seed=1, segment=50000, device=None, progress=None, lanes=0):
+           seed=1, segment=50000, device=None, progress=None, lanes=0, pack=None):
     """datasets: list of (concs, responses).  Returns dict with log_py[model] -> [n_pairs], B12 [n_pairs],
     means[model] -> [n_pairs, T] (averaged over replicates), acceptance[model] -> [n_pairs, T, R].
     Under torch.distributed (one process per GPU) the global chain list is sharded contiguously over the ranks and
-    every rank returns the full result; with a fixed `lanes` the result does not depend on the number of ranks."""
+    every rank returns the full result; with a fixed `lanes` the result does not depend on the number of ranks.
+    `pack`: the SinglePack of `datasets` if the caller already has it.  The whole call is ordered after the work
+    already queued on the current CUDA stream and is complete (host results in hand) when it returns, so CUDA events
+    recorded on the current stream around it time the sampling, the all-gathers and the integration."""
     import torch
     temps = temperature_ladder() if temps is None else np.asarray(temps, dtype=np.float64)
     ws, rank, local = phf_dist.world()
-    pack = SinglePack(datasets)
+    pack = SinglePack(datasets) if pack is None else pack
     n_pairs, T, R = len(datasets), len(temps), replicates
     num_saved = iterations // thinning + 1
     burn = num_saved // burn_in_fraction
     out = {"temps": temps, "means": {}, "log_py": {}, "acceptance": {}}
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     ids, tt = build_chain_list(n_pairs, temps, R)
-    n_groups = pack.datasets["n_groups"][ids].astype(np.float64)
-    bounds = phf_dist.shard_bounds(n_groups, ws)
+    bounds = phf_dist.shard_bounds(pack.dataset_cost()[ids], ws)   # ranks get equal work, not equal chain counts
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
     # the models are independent: their launches go to separate streams and share the SMs
     samplers, streams = {}, {}
+    cur = torch.cuda.current_stream(dev)
     if hi > lo:
         for model in models:
             d = 2 if model == 1 else 3
@@ -68,6 +71,8 @@ def run_ti(datasets, models=(1, 2), temps=None, replicates=1, iterations=500000,
             streams[model] = torch.cuda.Stream(device=dev)
         torch.cuda.synchronize(dev)
         t_start = time.perf_counter()
+        for model in models:
+            streams[model].wait_stream(cur)
         done = 0
         while done < iterations:
             k = min(segment, iterations - done)
@@ -77,8 +82,12 @@ def run_ti(datasets, models=(1, 2), temps=None, replicates=1, iterations=500000,
             done += k
             if progress:
                 progress(done, iterations)
+        for model in models:
+            cur.wait_stream(streams[model])
         torch.cuda.synchronize(dev)
         out["sample_seconds"] = time.perf_counter() - t_start   # this rank's sampling phase (launch to synchronise)
+    out["chains_local"] = (hi - lo) * len(models)
+    out["lanes"] = {m: samplers[m].lanes for m in samplers}
     t_gather = time.perf_counter()
     for model in models:
         d = 2 if model == 1 else 3

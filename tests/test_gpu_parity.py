@@ -88,6 +88,40 @@ def test_log_target_matches_oracle_random(table, single_pack, model):
         assert_close(l1.cpu().numpy(), want1, what="%s/%s ll1" % (drug, channel))
 
 
+@pytest.mark.parametrize("model", [1, 2])
+def test_log_target_synthetic_config5_datasets_vs_oracle(model):
+    """BASELINE config 5's data path: 12 000 synthetic datasets (5 experiments x 4 doses, responses rounded to one
+    decimal and clipped to [0, 100]) packed by the VECTORISED packer SinglePack.from_uniform, two parameter vectors
+    per dataset (one near the generating values, one anywhere incl. out of support), random ladder temperatures --
+    against the C oracle evaluated on each dataset's raw (concs, responses)."""
+    from pyhillfit_b200 import synthetic
+    from pyhillfit_b200.packing import SinglePack
+    from pyhillfit_b200.sampler import log_target_batch
+    n_ds = 12000
+    concs, Y, truth = synthetic.generate(n_ds, offset=777)
+    pack = SinglePack.from_uniform(concs, Y)
+    rng = np.random.default_rng(55 + model)
+    near = truth * (1.0 + 0.05 * rng.standard_normal(truth.shape))
+    far = np.stack([rng.uniform(-3.5, 11, n_ds), rng.uniform(-0.2, 10.2, n_ds),
+                    np.exp(rng.uniform(np.log(8e-4), np.log(50.), n_ds))], 1)
+    th = np.concatenate([near, far])
+    th = th if model == 2 else np.ascontiguousarray(th[:, [0, 2]])
+    ids = np.tile(np.arange(n_ds, dtype=np.int32), 2)
+    ladder = ho.temperature_ladder()
+    tt = ladder[rng.integers(0, len(ladder), len(ids))]
+    tt[:n_ds:3] = 1.0
+    lt, l1 = log_target_batch(model, pack, th, ids, tt)
+    lt, l1 = lt.cpu().numpy(), l1.cpu().numpy()
+    want, want1 = np.empty(len(ids)), np.empty(len(ids))
+    pb = ho.compute_pi_bit_of_log_likelihood(concs)
+    for k in range(len(ids)):
+        w, w1 = c_oracle.log_target_batch(model, concs, Y[ids[k]], th[k][None], tt[k], pb)
+        want[k], want1[k] = w[0], w1[0]
+    assert np.isfinite(want[:n_ds]).mean() > 0.95 and (Y == 0).sum() > 1000 and (Y == 100).sum() > 100
+    assert_close(lt, want, what="synthetic log_target")
+    assert_close(l1, want1, what="synthetic loglik_t1")
+
+
 def test_doseresponse_scalar_api(table):
     """The reference's own call signatures (dr.log_target & co.) on SURVEY 8c's known answers."""
     import pyhillfit_b200.doseresponse as dr

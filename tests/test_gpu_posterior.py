@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from _data import GOLD, Table
+from _stats import assert_quantiles_within_mcse
 
 pytestmark = pytest.mark.gpu
 
@@ -21,7 +22,8 @@ def table():
                                                 ("Amiodarone", "hERG", 1)])
 def test_hierarchical_posterior_matches_reference_chain(table, drug, channel, lanes):
     """(lanes = 0: the lane-per-parameter kernel; 1: the thread-per-chain kernel.)  64 GPU chains vs one reference chain (python/PyHillFit.py:481-511 loop + :173-193 target, numpy RNG, 2e5
-    iterations): 5/25/50/75/95 % quantiles of all 5+2Ne parameters within 5 standard errors of the reference chain's quantile estimates."""
+    iterations): 5/25/50/75/95 % quantiles of all 5+2Ne parameters within 4 Monte-Carlo standard errors of the quantile
+    estimates (tests/_stats.py)."""
     from pyhillfit_b200.packing import HierPack
     from pyhillfit_b200.sampler import HierarchicalSampler, hier_priors
     g = np.load(os.path.join(GOLD, "ref_chains.npz"))
@@ -38,13 +40,8 @@ def test_hierarchical_posterior_matches_reference_chain(table, drug, channel, la
     burn = (iters // thin + 1) // 4
     d = len(theta0)
     pooled = smp[:, burn:, :d].reshape(-1, d)
-    q = np.percentile(pooled, [5, 25, 50, 75, 95], axis=0)
-    # MCSE of a quantile estimate = sqrt(p(1-p)/ESS_p) / density: for a normal shape that is (2.11, 1.36, 1.25, 1.36,
-    # 2.11) x sd/sqrt(ESS) at the 5/25/50/75/95 % points; the ESS of a tail indicator is below the ESS of the mean the
-    # fixture records, hence the extra factor 1.5.  Tolerance: 5 such standard errors of the REFERENCE chain.
-    f = 1.5 * np.array([2.11, 1.36, 1.25, 1.36, 2.11])
-    tol = 5.0 * f[:, None] * (g[key + "_sd"] / np.sqrt(g[key + "_ess"]))[None, :]
-    assert np.all(np.abs(q - g[key + "_q"]) <= tol), np.abs(q - g[key + "_q"]) / tol
+    # 4 Monte-Carlo standard errors of the quantile estimates (tail-indicator ESS of both sides: tests/_stats.py)
+    assert_quantiles_within_mcse(smp[:, burn:, :d], g[key + "_q"], g[key + "_ess_q"], 4.0, key)
     acc = s.acceptance()
     assert 0.1 < acc.mean() < 0.45
     # the reference repository's own shipped (alpha, mu) draws for this pair (500 samples, Oct-2016 code): means
@@ -56,15 +53,20 @@ def test_hierarchical_posterior_matches_reference_chain(table, drug, channel, la
     assert abs(pooled[:, 2].mean() - m_mean) <= 4 * m_sd / np.sqrt(250) + 0.02
 
 
-def test_bayes_factor_matches_reference_pipeline(table):
+@pytest.mark.parametrize("drug,channel,tag", [("Amiodarone", "hERG", "ladder"), ("Bepridil", "hERG", "ladder2")])
+def test_bayes_factor_matches_reference_pipeline(table, drug, channel, tag):
     """Fused thermodynamic integration (41-point ladder, in-kernel accumulation of the temperature-1
-    log-likelihood, all-gather, trapezium) vs PyHillTemp.py + compute_bayes_factors.py on reference chains.
-    Tolerance: 5 combined Monte-Carlo standard errors of the two integrals (stated below), B12 accordingly."""
+    log-likelihood, all-gather, trapezium) vs PyHillTemp.py + compute_bayes_factors.py on reference chains, for a
+    plain pair and for one with two responses at 100 (the logsf branch, doseresponse.py:219,245).
+    Tolerance: 4 combined Monte-Carlo standard errors of the two integrals (stated below), B12 accordingly."""
     from pyhillfit_b200 import ti
     g = np.load(os.path.join(GOLD, "ref_chains.npz"))
     temps = g["temps"]
+    sfx = "" if tag == "ladder" else "_" + tag
+    g = {**{k: g[k] for k in g.files}, **{k.replace(tag + "_", "ladder_"): g[k] for k in g.files if k.startswith(tag + "_")},
+         "log_py_m1": g["log_py_m1" + sfx], "log_py_m2": g["log_py_m2" + sfx], "B12": g["B12" + sfx]}
     R = 16
-    out = ti.run_ti([table.concat("Amiodarone", "hERG")], temps=temps, replicates=R, iterations=100000, thinning=5,
+    out = ti.run_ti([table.concat(drug, channel)], temps=temps, replicates=R, iterations=100000, thinning=5,
                     burn_in_fraction=4, seed=31, segment=50000)
     w = np.zeros(len(temps))
     w[1:] += 0.5 * np.diff(temps)
@@ -76,10 +78,10 @@ def test_bayes_factor_matches_reference_pipeline(table):
         var_gpu = np.sum(w ** 2 * per_rep.var(axis=1, ddof=1) / R)
         se = float(np.sqrt(var_ref + var_gpu))
         diff[m] = (float(out["log_py"][m][0]) - float(g["log_py_m%d" % m]), se)
-        assert abs(diff[m][0]) <= 5 * se, (m, diff[m])
+        assert abs(diff[m][0]) <= 4 * se, (m, diff[m])
         assert se < 0.2
     se12 = float(np.hypot(diff[1][1], diff[2][1]))
-    assert abs(np.log(out["B12"][0]) - np.log(float(g["B12"]))) <= 5 * se12
+    assert abs(np.log(out["B12"][0]) - np.log(float(g["B12"]))) <= 4 * se12
     acc = out["acceptance"][2][0]
     assert np.all(acc[5:] > 0.1) and np.all(acc < 0.6)
 
@@ -105,3 +107,145 @@ def test_prior_only_chain_samples_the_prior(table):
     assert np.all(smp[:, :, 3] == -0.2 * smp[:, :, 0] + 4 * np.log(smp[:, :, 2] - 1e-3) - (smp[:, :, 2] - 1e-3) / 1.49975) \
         or np.allclose(smp[:, :, 3], -0.2 * smp[:, :, 0] + 4 * np.log(smp[:, :, 2] - 1e-3) - (smp[:, :, 2] - 1e-3) / 1.49975,
                        rtol=1e-12, atol=1e-12)
+
+
+FIT_CASES = [(dg, ch, m) for dg, ch in (("Amiodarone", "hERG"), ("Bepridil", "hERG"), ("Amitriptyline", "Kv4.3"))
+             for m in (1, 2)]
+
+
+@pytest.mark.parametrize("drug,channel,model", FIT_CASES)
+def test_fit_variant_posterior_matches_reference_target_chain(table, drug, channel, model):
+    """The PyHillFit-variant loop (python/PyHillFit.py:748-751, 787-856: Sigma0 = 0.05 diag|theta0|, adaptation after
+    1000 d iterations, no mean reset): 64 GPU chains vs a chain of the reference's own dr.log_target driven by the
+    oracle's restatement of that loop with numpy's RNG and npr.seed(25) (tests/golden/ref_chains.npz `fit_*`, made by
+    oracle/gen_golden_chains.py).  Pairs: plain; two responses at 100 (logsf branch, doseresponse.py:219,245); the
+    dropped -2.6 response (data/crumb_data.csv:155).  Quantiles within 4 MCSE (tests/_stats.py)."""
+    from pyhillfit_b200.packing import SinglePack
+    from pyhillfit_b200.sampler import SingleLevelSampler
+    g = np.load(os.path.join(GOLD, "ref_chains.npz"))
+    key = "fit_%s_%s_m%d" % (drug, channel.replace(".", "_"), model)
+    theta0, iters, thin = g[key + "_theta0"], int(g[key + "_iters"]), int(g["thin"])
+    d = len(theta0)
+    nch = 64
+    pack = SinglePack([table.concat(drug, channel)])
+    s = SingleLevelSampler(model, pack, np.zeros(nch, dtype=np.int32), 1.0, np.tile(theta0, (nch, 1)), variant="fit",
+                           seed=25, thinning=thin)
+    row0 = s.initial_row().cpu().numpy()
+    smp = s.run(iters).cpu().numpy()
+    saved = iters // thin + 1
+    burn = saved // int(g["burn_frac"])
+    post = smp[:, burn - 1:, :]            # smp row k is saved row k+1: rows burn.. of the chain (PyHillFit.py:861-864)
+    assert post.shape[1] == saved - burn
+    assert_quantiles_within_mcse(post[:, :, :d], g[key + "_q"], g[key + "_ess_q"], 4.0, key)
+    # mean log-target of the post-burn rows: a scalar summary of the whole posterior (its own MC error on both sides)
+    lt = post[:, :, d]
+    se = np.hypot(lt.mean(axis=1).std(ddof=1) / np.sqrt(nch), lt.std() / np.sqrt(max(float(g[key + "_ess"].min()), 1.0)))
+    assert abs(lt.mean() - float(g[key + "_lt_mean"])) <= 4 * se
+    assert abs(s.acceptance().mean() - float(g[key + "_acc"])) < 0.05
+    assert np.all(row0[:, :d] == theta0)
+
+
+@pytest.mark.parametrize("drug,channel,model", [("Bepridil", "hERG", 2), ("Amitriptyline", "Kv4.3", 2),
+                                                ("Bepridil", "hERG", 1)])
+def test_extra_pairs_match_reference_do_mcmc(table, drug, channel, model):
+    """The reference's own do_mcmc (python/PyHillTemp.py:57-125) at temperature 1 for a pair with two responses at 100
+    and for the pair with the dropped -2.6 response (`extra_*` in tests/golden/ref_chains.npz): quantiles within 4
+    MCSE and the mean temperature-1 log-likelihood (what compute_bayes_factors.py:11-27 averages) within 4 combined
+    standard errors."""
+    from pyhillfit_b200.packing import SinglePack
+    from pyhillfit_b200.sampler import SingleLevelSampler
+    g = np.load(os.path.join(GOLD, "ref_chains.npz"))
+    key = "extra_%s_%s_m%d" % (drug, channel.replace(".", "_"), model)
+    d = 2 if model == 1 else 3
+    nch, iters, thin = 64, int(g["iters"]), int(g["thin"])
+    saved = iters // thin + 1
+    burn = saved // int(g["burn_frac"])
+    pack = SinglePack([table.concat(drug, channel)])
+    s = SingleLevelSampler(model, pack, np.zeros(nch, dtype=np.int32), 1.0, np.ones((nch, d)), variant="temp", seed=77,
+                           thinning=thin, burn_rows=burn)
+    smp = s.run(iters).cpu().numpy()[:, burn - 1:, :]
+    assert_quantiles_within_mcse(smp[:, :, :d], g[key + "_q"], g[key + "_ess_q"], 4.0, key)
+    ll1 = s.loglik_t1_mean()
+    ref_se = float(g[key + "_ll1_sd"]) / np.sqrt(float(g[key + "_ll1_ess"]))
+    assert abs(ll1.mean() - float(g[key + "_ll1_mean"])) <= 4 * np.hypot(ref_se, ll1.std(ddof=1) / np.sqrt(nch))
+
+
+def test_config3_full_size_alpha_mu_vs_all_210_shipped_sample_files(table):
+    """BASELINE config 3 at full size -- the hierarchical model for every Crumb pair, 256 chains each (53 760 chains,
+    dim 11..17), 2e5 iterations -- against the ONLY result fixture the reference repository ships: the 210 files
+    chaste/samples/<drug>_<channel>_hill_pic50_samples.txt (500 post-burn (alpha, mu) draws each, written by
+    python/PyHillFit.py:519-525 from a 5e5-iteration chain of Oct-2016 code; tests/golden/chaste_alpha_mu_summary.npz
+    holds their mean and sd).  Start points: the repository's `hierarchical_start` (the reference's CMA-ES is absent).
+
+    Tolerance per pair and parameter: |mean_gpu - mean_ref| <= 4 * sd_ref / sqrt(250) + 0.02, i.e. 4 standard errors
+    of a mean of 500 draws taken from one autocorrelated chain (n_eff = 250: the draws are distinct rows of one chain
+    whose own Monte-Carlo error adds to the sampling error of 500 draws), plus 0.02 for the GPU side and for the
+    unknown code version of the shipped files.  The count of pairs inside it is reported (gpurun_out/) and must be
+    >= 200 of 210 for alpha and for mu; the posterior sds must agree within a factor 1.5 for >= 200 pairs."""
+    import json
+    import torch
+    from pyhillfit_b200.packing import HierPack
+    from pyhillfit_b200.PyHillFit import hierarchical_start
+    from pyhillfit_b200.initial_fit import best_fit_batch
+    from pyhillfit_b200.sampler import HierarchicalSampler, hier_priors
+    pr, shapes, scales, locs = hier_priors()
+    pairs = table.pairs()
+    c = np.load(os.path.join(GOLD, "chaste_alpha_mu_summary.npz"))
+    assert list(c["pairs_drug"]) == [p[0] for p in pairs] and list(c["pairs_channel"]) == [p[1] for p in pairs]
+    ex_all = [table.experiments(*p) for p in pairs]
+    fits, _ = best_fit_batch(2, [(e[:, 0], e[:, 1]) for ex in ex_all for e in ex], pic50_lower=-2.0)
+    at, starts = 0, []
+    for ex in ex_all:
+        starts.append(hierarchical_start(ex, locs, fits[at:at + len(ex)]))
+        at += len(ex)
+    by_ne = {}
+    for ip, ex in enumerate(ex_all):
+        by_ne.setdefault(len(ex), []).append(ip)
+    nch, iters, thin, seg = 256, 200000, 5, 4000
+    saved = iters // thin + 1
+    burn = saved // 4
+    got = np.full((len(pairs), 4), np.nan)       # mean alpha, sd alpha, mean mu, sd mu
+    n_chains = 0
+    for ne, idxs in sorted(by_ne.items()):
+        pack = HierPack([ex_all[i] for i in idxs])
+        ids = np.repeat(np.arange(len(idxs), dtype=np.int32), nch)
+        theta0 = np.repeat(np.stack([starts[i] for i in idxs]), nch, axis=0)
+        s = HierarchicalSampler(pack, ids, theta0, pr, seed=1000 + ne, thinning=thin)
+        n_chains += s.n
+        buf = torch.empty((seg // thin, s.n, s.d + 1), dtype=torch.float64, device=s.device)
+        sums = torch.zeros((4, s.n), dtype=torch.float64, device=s.device)   # sum a, sum a^2, sum mu, sum mu^2
+        count, row = 0, 0
+        for _ in range(iters // seg):
+            smp = s.run(seg, samples=buf, row_major=True)                    # [rows, n, d+1], rows row+1 .. row+rows
+            first = max(burn - (row + 1), 0)
+            if first < smp.shape[0]:
+                a, m = smp[first:, :, 0], smp[first:, :, 2]
+                sums[0] += a.sum(0); sums[1] += (a * a).sum(0); sums[2] += m.sum(0); sums[3] += (m * m).sum(0)
+                count += smp.shape[0] - first
+            row += smp.shape[0]
+        assert count == saved - burn
+        per_pair = sums.reshape(4, len(idxs), nch).sum(2).cpu().numpy() / (count * nch)
+        got[idxs, 0] = per_pair[0]
+        got[idxs, 1] = np.sqrt(np.maximum(per_pair[1] - per_pair[0] ** 2, 0))
+        got[idxs, 2] = per_pair[2]
+        got[idxs, 3] = np.sqrt(np.maximum(per_pair[3] - per_pair[2] ** 2, 0))
+        acc = s.acceptance()
+        assert 0.05 < acc.mean() < 0.5
+    assert n_chains == 53760
+    ref = c["summary"]
+    tol_a = 4 * ref[:, 1] / np.sqrt(250) + 0.02
+    tol_m = 4 * ref[:, 3] / np.sqrt(250) + 0.02
+    in_a = np.abs(got[:, 0] - ref[:, 0]) <= tol_a
+    in_m = np.abs(got[:, 2] - ref[:, 2]) <= tol_m
+    sd_ok = (np.abs(np.log(got[:, 1] / ref[:, 1])) < np.log(1.5)) & (np.abs(np.log(got[:, 3] / ref[:, 3])) < np.log(1.5))
+    report = {"pairs": len(pairs), "alpha_within": int(in_a.sum()), "mu_within": int(in_m.sum()), "sd_within_1.5x": int(sd_ok.sum()),
+              "alpha_z_abs_median": float(np.median(np.abs(got[:, 0] - ref[:, 0]) / (ref[:, 1] / np.sqrt(250)))),
+              "mu_z_abs_median": float(np.median(np.abs(got[:, 2] - ref[:, 2]) / (ref[:, 3] / np.sqrt(250)))),
+              "outside": [[pairs[i][0], pairs[i][1], [float(x) for x in got[i]], [float(x) for x in ref[i]]]
+                          for i in np.nonzero(~(in_a & in_m))[0]]}
+    out_dir = os.path.join(os.path.dirname(GOLD), "..", "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "config3_vs_chaste_all_pairs.json"), "w") as f:
+            json.dump(report, f, indent=1)
+    print("config 3 vs chaste/samples:", {k: v for k, v in report.items() if k != "outside"})
+    assert in_a.sum() >= 200 and in_m.sum() >= 200 and sd_ok.sum() >= 200, report

@@ -305,3 +305,26 @@ def test_batched_initial_fit_matches_the_scalar_one(table):
         rt, rs = best_fit(2, e[:, 0], e[:, 1], pic50_lower=-2.0)
         assert abs(ss[k] - rs) <= 1e-6 * max(rs, 1.0)
     assert best_fit_batch(2, [])[0].shape == (0, 3)
+
+
+def test_from_uniform_packer_equals_scalar_packer():
+    """SinglePack.from_uniform (the vectorised packer of BASELINE config 5) == SinglePack([...]) (pack_single_one per
+    dataset), field by field and bit for bit, on synthetic config-5 datasets including ones with responses clipped to
+    0 and to 100, a dose whose replicates are all censored, and an out-of-range response."""
+    from pyhillfit_b200 import synthetic
+    from pyhillfit_b200.packing import SinglePack
+    concs, Y, _ = synthetic.generate(400, seed=3)
+    Y = Y.copy()
+    Y[0, :] = 0.0                      # every response censored at 0
+    Y[1, :] = 100.0                    # ... at 100
+    Y[2, 0] = -2.6                     # in no mask (data/crumb_data.csv:155), still counted in pi_bit
+    Y[3, concs == concs[0]] = 0.0      # one whole dose censored
+    Y[4, :2] = [0.0, 100.0]            # zeros and hundreds in one dataset
+    fast = SinglePack.from_uniform(concs, Y)
+    slow = SinglePack([(concs, Y[k]) for k in range(len(Y))])
+    assert fast.n_datasets == slow.n_datasets == len(Y)
+    for f in fast.datasets.dtype.names:
+        assert np.array_equal(fast.datasets[f], slow.datasets[f]), f
+    assert len(fast.groups) == len(slow.groups)
+    for f in fast.groups.dtype.names:
+        assert np.array_equal(fast.groups[f], slow.groups[f]), f

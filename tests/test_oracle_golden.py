@@ -186,3 +186,66 @@ def test_cdf_oracle_matches_reference_golden():
         out = ho.construct_posterior_predictive_cdfs(full[:, 0], full[:, 1], full[:, 2], full[:, 3])
     for got, key in zip(out, ("hill_x", "hill_cdf", "pic50_x", "pic50_cdf", "hill_pdf", "pic50_pdf")):
         assert np.array_equal(got, g[key]), key
+
+
+def test_am_hier_c_oracle_follows_py_oracle(table):
+    """The C hierarchical AM loop (oracle/hill_oracle.c: what every GPU hierarchical trajectory test is compared with)
+    is pinned to the numpy restatement of python/PyHillFit.py:431-511 driven by the restated target of
+    python/PyHillFit.py:173-193 (itself pinned to the unmodified reference by hier_target_golden.npz), on the same
+    Philox stream: Ne = 3 (dim 11) and Ne = 5 (dim 15), across the start of adaptation."""
+    shapes, scales, locs = ho.hier_prior_constants()
+    for drug, channel in (("Amiodarone", "hERG"), ("Dofetilide", "hERG")):
+        ex = table.experiments(drug, channel)
+        ne = len(ex)
+        theta0 = np.concatenate(([1.1, 4.2, 6.0, 0.3], np.tile([6.0, 1.0], ne) + 0.05 * np.arange(2 * ne), [7.0]))
+        cov0, _, reset = ho.am_defaults("hier", theta0)
+        adapt_when, iters, thin, seed, cid = 40, 300, 5, 11, 5
+
+        def target(th):
+            with np.errstate(all="ignore"):
+                return ho.hier_log_target(ex, th, shapes, scales, locs)
+
+        orig = ho.am_defaults
+        ho.am_defaults = lambda v, t0: (cov0.copy(), adapt_when, reset)
+        try:
+            chain_py, acc = ho.adaptive_metropolis(target, theta0, iters, thin, "hier", rng="philox", seed=seed,
+                                                   chain_id=cid)
+        finally:
+            ho.am_defaults = orig
+        lt0 = c_oracle.hier_log_target_batch(ex, theta0[None, :], shapes, scales, locs)[0]
+        assert lt0 == pytest.approx(target(theta0), rel=1e-12)
+        st = c_oracle.make_state(theta0, lt0, 0.0, cov0)
+        chain_c = c_oracle.am_hier(ex, shapes, scales, locs, st, 0, iters, thin, adapt_when, seed, cid)
+        assert np.allclose(chain_c, chain_py[1:], rtol=1e-8, atol=1e-8), (drug, channel)
+        assert st[-1] / iters == pytest.approx(acc, abs=1e-12)
+        assert 0.02 < acc < 0.9
+
+
+def test_am_zero_start_component_freezes_that_coordinate(table):
+    """theta0 with a component of exactly 0 (Sigma0 = 0.05 diag|theta0| then has a zero variance, PyHillFit.py:751):
+    the reference's SVD-based draw leaves that coordinate where it is and moves the others.  The Cholesky-based Philox
+    path (C oracle == numpy restatement == GPU kernels) stores the zero diagonal as COV0_DIAG_FLOOR: same behaviour,
+    no NaN."""
+    concs, y = table.concat("Amiodarone", "hERG")
+    w0, w100, wo = ho.masks(y)
+    pb = ho.compute_pi_bit_of_log_likelihood(wo)
+    theta0 = np.array([6.0, 0.0, 7.0])          # Hill exactly 0: in support, zero proposal variance
+
+    def target(th):
+        with np.errstate(all="ignore"):
+            return ho.log_target(2, y, w0, w100, wo, concs, th, 1, pb)
+
+    chain_py, acc = ho.adaptive_metropolis(target, theta0, 400, 5, "fit", rng="philox", seed=4, chain_id=1)
+    assert np.all(np.isfinite(chain_py)) and acc > 0.05
+    assert np.all(np.abs(chain_py[:, 1]) < 1e-20)                     # frozen
+    assert np.ptp(chain_py[:, 0]) > 1e-3 and np.ptp(chain_py[:, 2]) > 1e-3   # the others move
+    cov0, adapt_when, reset = ho.am_defaults("fit", theta0)
+    lt0, ll10 = c_oracle.log_target_batch(2, concs, y, theta0[None, :], 1.0, pb)
+    st = c_oracle.make_state(theta0, lt0[0], ll10[0], cov0)
+    chain_c = c_oracle.am_single(2, concs, y, 1.0, pb, st, 0, 400, 5, adapt_when, reset, 4, 1)
+    assert np.allclose(chain_c, chain_py[1:], rtol=1e-9, atol=1e-9)
+    # the reference's own draw (numpy multivariate_normal, SVD factor) freezes the coordinate exactly
+    import numpy.random as npr
+    npr.seed(25)
+    chain_np, _ = ho.adaptive_metropolis(target, theta0, 400, 5, "fit", rng="numpy")
+    assert np.all(np.abs(chain_np[:, 1]) < 1e-12) and np.ptp(chain_np[:, 0]) > 1e-3
