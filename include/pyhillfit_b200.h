@@ -123,7 +123,15 @@ typedef struct phf_am_config {
                                     python/PyHillTemp.py:125 drop before saving.  `samples` then starts at row
                                     max(burn_rows, first row of this call).  0: every saved row is written (the
                                     hierarchical loop keeps its burn-in: python/PyHillFit.py:514-515). */
-    int32_t reserved;            /* must be 0 */
+    int32_t speculation;         /* single-level only.  Depth S of speculative (prefetching) evaluation: S groups of
+                                    lanes_per_chain lanes evaluate the proposals of the next S iterations at once, each
+                                    under the hypothesis that its predecessors are rejected (acceptance is steered to
+                                    0.25), and the chain advances to the first accepted one -- 2.7 iterations per round
+                                    at S = 4 for the latency of ~1.2: the form for launches with too few chains to fill
+                                    the GPU (a sharded thermodynamic-integration sweep).  1: none; 2, 4, 8 (lanes x S
+                                    <= 32); 0: chosen from the chain count (phf_am_single_speculation).  The chain is THE
+                                    SAME, bit for bit, as with speculation = 1 and the same lanes_per_chain: a tuning
+                                    knob like the CTA size (csrc/phf_single_spec.cu). */
 } phf_am_config;
 #define PHF_SAMPLES_CHAIN_MAJOR 0
 #define PHF_SAMPLES_ROW_MAJOR 1
@@ -141,6 +149,14 @@ int phf_am_single_init(int model, int64_t n_chains, const double *theta0 /* [n,d
 /* lanes per chain the library picks for `n_chains` resident chains when cfg->lanes_per_chain == 0 (current device);
  * pass the total over all launches that run concurrently */
 int phf_am_single_lanes(int64_t n_chains);
+
+/* speculation depth the library picks for `n_chains` resident chains of `lanes` lanes each when cfg->speculation == 0 */
+int phf_am_single_speculation(int64_t n_chains, int lanes);
+
+/* (lanes_per_chain, speculation) the sampler will run with for `n_chains` concurrently running chains, given the
+ * caller's cfg values (0 = choose; both 0: chosen together) */
+int phf_am_single_shape(int64_t n_chains, int32_t lanes, int32_t speculation, int32_t *lanes_out,
+                        int32_t *speculation_out);
 
 /* resident CTAs per SM of the sampler kernel for (model, lanes per chain) at a CTA size and dynamic shared-memory
  * size on the current device (the runtime's occupancy calculator; a tuning query, < 0 on error) */

@@ -24,7 +24,7 @@ class AmConfig(C.Structure):
                 ("burn_rows", C.c_uint32), ("rows_capacity", C.c_uint32), ("seed", C.c_uint64),
                 ("chain_id_base", C.c_uint64), ("stage_groups", C.c_int32), ("block_threads", C.c_int32),
                 ("lanes_per_chain", C.c_int32), ("min_ctas_hint", C.c_int32), ("sample_layout", C.c_int32),
-                ("cta_order", C.c_int32), ("discard_burn_rows", C.c_int32), ("reserved", C.c_int32)]
+                ("cta_order", C.c_int32), ("discard_burn_rows", C.c_int32), ("speculation", C.c_int32)]
 
 
 SAMPLES_CHAIN_MAJOR, SAMPLES_ROW_MAJOR = 0, 1
@@ -47,7 +47,7 @@ assert DOSE_GROUP_DTYPE.itemsize == 64 and DATASET_DTYPE.itemsize == 32
 assert HIER_POINT_DTYPE.itemsize == 32 and HIER_DATASET_DTYPE.itemsize == 16
 
 EXPORTS = ["phf_log_target_batch", "phf_am_single_init", "phf_am_single_run", "phf_am_single_lanes",
-           "phf_am_single_resident_ctas", "phf_hier_log_target_batch",
+           "phf_am_single_speculation", "phf_am_single_shape", "phf_am_single_resident_ctas", "phf_hier_log_target_batch",
            "phf_am_hier_init", "phf_am_hier_run", "phf_am_single_run_host", "phf_am_hier_run_host",
            "phf_release_workspaces",
            "phf_write_rows_text_host",
@@ -78,6 +78,8 @@ def load():
     L.phf_log_target_batch.argtypes = [C.c_int, C.c_int64, _p, _p, _p, _p, _p, _p, _p, _p]
     L.phf_am_single_init.argtypes = [C.c_int, C.c_int64, _p, _p, _p, _p, _p, _p, _p, _p]
     L.phf_am_single_lanes.argtypes = [C.c_int64]
+    L.phf_am_single_speculation.argtypes = [C.c_int64, C.c_int]
+    L.phf_am_single_shape.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.phf_am_single_resident_ctas.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64]
     L.phf_am_single_run.argtypes = [C.POINTER(AmConfig), C.c_int64, _p, _p, _p, _p, _p, _p, _p]
     L.phf_hier_log_target_batch.argtypes = [C.c_int64, _p, C.c_int32, _p, _p, _p, C.POINTER(HierPriors), _p, _p]

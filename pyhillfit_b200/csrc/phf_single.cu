@@ -93,35 +93,6 @@ __global__ void __launch_bounds__(128) am_single_init_kernel(int64_t n, const do
 // instruction chain of one iteration ~3x for launches with too few chains to fill the SMs.
 // The CTA's datasets are staged once in shared memory; HBM is touched only for the thinned rows.
 // ------------------------------------------------------------------------------------------------
-template <int D>
-struct Draws {
-    double log_u;  // log of the accept uniform
-    double z[D];   // standard normals
-};
-
-template <int D>
-PHF_DI Draws<D> make_draws(const double *T, uint64_t seed, uint64_t chain_id, uint32_t t)
-{
-    Draws<D> dr;
-    const Philox4 r0 = philox_call(seed, chain_id, t, 0u);
-    dr.log_u = fm::log_pos(T, uniform53(r0.w[0], r0.w[1]));
-    box_muller(T, r0.w[2], r0.w[3], dr.z[0], dr.z[1]);
-    if (D == 3) {
-        const Philox4 r1 = philox_call(seed, chain_id, t, 1u);
-        double unused;
-        box_muller(T, r1.w[0], r1.w[1], dr.z[D - 1], unused);
-    }
-    return dr;
-}
-
-// Registers of one chain (identical on the G lanes that own it).
-template <int MODEL>
-struct ChainRegs {
-    static constexpr int D = SingleDims<MODEL>::D, NT = SingleDims<MODEL>::NT;
-    double th[D], mean[D], cov[NT];
-    double lt, l1, loga, l1_sum, n_acc;
-};
-
 // Per-launch constants of one chain.
 struct ChainConst {
     const phf_dose_group *grp;
@@ -142,23 +113,7 @@ PHF_DI void am_step(const double *T, const ChainConst &cc, ChainRegs<MODEL> &s, 
     constexpr int D = SingleDims<MODEL>::D;
     // ---- proposal theta* = theta + e^{loga/2} chol(cov) z  (N(theta, e^loga cov): PyHillFit.py:831) ----
     double star[D];
-    {
-        const double sc = fm::exp_clamped(T, 0.5 * s.loga);
-        const double r0 = fm::rsqrt(s.cov[0]);
-        const double l00 = s.cov[0] * r0, l10 = s.cov[1] * r0;
-        const double s11 = guarded_pivot(fma(-l10, l10, s.cov[2]), s.cov[2]);
-        const double r1 = fm::rsqrt(s11);
-        const double l11 = s11 * r1;
-        star[0] = fma(sc, l00 * dr.z[0], s.th[0]);
-        star[1] = fma(sc, fma(l10, dr.z[0], l11 * dr.z[1]), s.th[1]);
-        if (D == 3) {
-            const double l20 = s.cov[3] * r0;
-            const double l21 = fma(-l20, l10, s.cov[4]) * r1;
-            const double s22 = guarded_pivot(fma(-l21, l21, fma(-l20, l20, s.cov[5])), s.cov[5]);
-            const double l22 = s22 * fm::rsqrt(s22);
-            star[D - 1] = fma(sc, fma(l20, dr.z[0], fma(l21, dr.z[1], l22 * dr.z[D - 1])), s.th[D - 1]);
-        }
-    }
+    propose<MODEL>(T, s.th, s.cov, s.loga, dr.z, star);
 
     // ---- target, accept (PyHillFit.py:833-838) ----
     double lt_star, l1_star;
@@ -438,6 +393,11 @@ static int launch_am_single(const phf_am_config &cfg, int64_t n, int block, size
     return check_launch("am_single_kernel");
 }
 
+// phf_single_spec.cu: the speculative (prefetching) form, lanes x depth lanes per chain
+int am_single_spec_launch(const phf_am_config &cfg, int lanes, int depth, int64_t n, int block, double *state,
+                          const int32_t *dataset_id, const double *temperature, const phf_dataset *datasets,
+                          const phf_dose_group *groups, double *samples, cudaStream_t s);
+
 }  // namespace phf
 
 using namespace phf;
@@ -503,6 +463,49 @@ extern "C" int phf_am_single_lanes(int64_t n_chains)
     return 1;
 }
 
+extern "C" int phf_am_single_speculation(int64_t n_chains, int lanes)
+{
+    // Speculation multiplies the lanes of a chain by S and commits (1 - 0.75^S) / 0.25 = 1.75 / 2.73 / 3.6 iterations per
+    // round (S = 2 / 4 / 8 at acceptance 0.25) for ~1.45 x the latency of one iteration (every lane replays the reject
+    // updates of its hypothesis and takes part in the commit).  It pays while the extra lanes find idle issue slots:
+    // measured on B200 with models 1 and 2 co-resident (profiles/r02_spec_sweep.txt, cycles per iteration):
+    //   2 152 chains: 2 lanes x S=4 1110 (block 128) against 2025 for 4 lanes x S=1;   4 304: 1407 against 2038;
+    //   8 610: 2 lanes x S=2 2208 against 2257 (4 x 1) and 2447 (2 x 1);   17 220: no gain (2920 for 2 x 1).
+    // S = 8 never won: at 32 lanes per chain the replayed updates outweigh the 3.6 iterations per round.
+    const int64_t sms = sm_count();
+    if (lanes < 1) lanes = 1;
+    if (lanes * 4 <= 32 && n_chains * lanes * 4 <= sms * 256) return 4;
+    if (lanes * 2 <= 32 && n_chains * lanes * 2 <= sms * 256) return 2;
+    return 1;
+}
+
+// (lanes per evaluation, speculation depth) for `n_chains` concurrently running chains; inputs of 0 mean "choose"
+extern "C" int phf_am_single_shape(int64_t n_chains, int32_t lanes, int32_t speculation, int32_t *lanes_out,
+                                   int32_t *speculation_out)
+{
+    if (!lanes_out || !speculation_out) return set_error(PHF_EINVAL, "phf_am_single_shape: null output");
+    if (lanes != 0 && lanes != 1 && lanes != 2 && lanes != 4)
+        return set_error(PHF_EINVAL, "cfg.lanes_per_chain must be 0 (auto), 1, 2 or 4");
+    if (speculation != 0 && speculation != 1 && speculation != 2 && speculation != 4 && speculation != 8)
+        return set_error(PHF_EINVAL, "cfg.speculation must be 0 (auto), 1 (none), 2, 4 or 8");
+    if (lanes == 0 && speculation == 0) {
+        // chosen together: in the latency regime two lanes x four hypotheses beat four lanes x two (1407 against 1619
+        // cycles per iteration at 4 304 chains), so the 4-lane form is only taken when speculation is switched off
+        lanes = phf_am_single_lanes(n_chains);
+        if (lanes == 4) lanes = 2;
+        speculation = phf_am_single_speculation(n_chains, lanes);
+    } else if (lanes == 0) {
+        lanes = phf_am_single_lanes(n_chains);
+    } else if (speculation == 0) {
+        speculation = phf_am_single_speculation(n_chains, lanes);
+    }
+    if (lanes * speculation > 32 || (speculation == 8 && lanes == 1))
+        return set_error(PHF_EINVAL, "lanes_per_chain x speculation: 1, 2, 4 lanes x depth 2, 4 (8 with 2 or 4 lanes)");
+    *lanes_out = lanes;
+    *speculation_out = speculation;
+    return PHF_OK;
+}
+
 extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, double *state,
                                  const int32_t *dataset_id, const double *temperature, const phf_dataset *datasets,
                                  const phf_dose_group *groups, double *samples, void *stream)
@@ -519,15 +522,18 @@ extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, dou
         return set_error(PHF_EINVAL, "cfg.rows_capacity is smaller than the rows this call produces");
     if (n_chains == 0 || cfg->n_iters == 0) return PHF_OK;
 
-    int lanes = cfg->lanes_per_chain;
-    if (lanes == 0) lanes = phf_am_single_lanes(n_chains);
-    if (lanes != 1 && lanes != 2 && lanes != 4)
-        return set_error(PHF_EINVAL, "cfg.lanes_per_chain must be 0 (auto), 1, 2 or 4");
+    int32_t lanes = 0, depth = 0;
+    if (int rc = phf_am_single_shape(n_chains, cfg->lanes_per_chain, cfg->speculation, &lanes, &depth)) return rc;
     int block = cfg->block_threads;
-    if (block <= 0) block = default_block_threads(n_chains * lanes);
+    // (speculative form: 128-thread CTAs measured best at every size -- the warps of a CTA land on the four
+    //  sub-partitions of one SM, single-warp CTAs do not spread as evenly: 1110 against 1223 / 2126 cycles per iteration)
+    if (block <= 0) block = depth > 1 ? 128 : default_block_threads(n_chains * lanes);
     if (block % 32 != 0 || block > 128)
         return set_error(PHF_EINVAL, "cfg.block_threads must be a multiple of 32, at most 128");
     if (cfg->stage_groups < 0) return set_error(PHF_EINVAL, "cfg.stage_groups must be >= 0");
+    if (depth > 1)
+        return am_single_spec_launch(*cfg, lanes, depth, n_chains, block, state, dataset_id, temperature, datasets, groups,
+                                     samples, (cudaStream_t)stream);
     // staged dose groups + (lanes > 1) one draw slot of d+1 doubles per thread + 32 gamma_s per warp
     const size_t smem = (size_t)cfg->stage_groups * sizeof(phf_dose_group) +
                         (lanes > 1 ? (size_t)block * ((cfg->model == 1 ? 2 : 3) + 1) * sizeof(double) : 0) +

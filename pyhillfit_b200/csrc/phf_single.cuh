@@ -180,4 +180,60 @@ PHF_DI void single_log_target(const double *T, const double *th, const phf_dose_
                                              log_target, loglik_t1);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// pieces shared by the sampler kernels (phf_single.cu: one evaluation per iteration; phf_single_spec.cu: speculative)
+// ------------------------------------------------------------------------------------------------
+template <int D>
+struct Draws {
+    double log_u;  // log of the accept uniform
+    double z[D];   // standard normals
+};
+
+template <int D>
+PHF_DI Draws<D> make_draws(const double *T, uint64_t seed, uint64_t chain_id, uint32_t t)
+{
+    Draws<D> dr;
+    const Philox4 r0 = philox_call(seed, chain_id, t, 0u);
+    dr.log_u = fm::log_pos(T, uniform53(r0.w[0], r0.w[1]));
+    box_muller(T, r0.w[2], r0.w[3], dr.z[0], dr.z[1]);
+    if (D == 3) {
+        const Philox4 r1 = philox_call(seed, chain_id, t, 1u);
+        double unused;
+        box_muller(T, r1.w[0], r1.w[1], dr.z[D - 1], unused);
+    }
+    return dr;
+}
+
+// Registers of one chain (identical on the G lanes that own it).
+template <int MODEL>
+struct ChainRegs {
+    static constexpr int D = SingleDims<MODEL>::D, NT = SingleDims<MODEL>::NT;
+    double th[D], mean[D], cov[NT];
+    double lt, l1, loga, l1_sum, n_acc;
+};
+
+// proposal theta* = theta + e^{loga/2} chol(cov) z  (N(theta, e^loga cov): PyHillFit.py:831, PyHillTemp.py:88), guarded
+// pivots (phf_math.cuh); cov = lower triangle, row-major
+template <int MODEL>
+PHF_DI void propose(const double *T, const double *th, const double *cov, double loga, const double *z, double *star)
+{
+    constexpr int D = SingleDims<MODEL>::D;
+    const double sc = fm::exp_clamped(T, 0.5 * loga);
+    const double r0 = fm::rsqrt(cov[0]);
+    const double l00 = cov[0] * r0, l10 = cov[1] * r0;
+    const double s11 = guarded_pivot(fma(-l10, l10, cov[2]), cov[2]);
+    const double r1 = fm::rsqrt(s11);
+    const double l11 = s11 * r1;
+    star[0] = fma(sc, l00 * z[0], th[0]);
+    star[1] = fma(sc, fma(l10, z[0], l11 * z[1]), th[1]);
+    if (D == 3) {
+        const double l20 = cov[3] * r0;
+        const double l21 = fma(-l20, l10, cov[4]) * r1;
+        const double s22 = guarded_pivot(fma(-l21, l21, fma(-l20, l20, cov[5])), cov[5]);
+        const double l22 = s22 * fm::rsqrt(s22);
+        star[D - 1] = fma(sc, fma(l20, z[0], fma(l21, z[1], l22 * z[D - 1])), th[D - 1]);
+    }
+}
+
 }  // namespace phf

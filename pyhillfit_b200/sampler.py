@@ -87,7 +87,7 @@ class _Base:
                              chain_id_base=int(self.chain_id_base), stage_groups=int(self.stage_groups),
                              block_threads=int(self.block_threads), lanes_per_chain=int(getattr(self, "lanes", 0)),
                              min_ctas_hint=int(getattr(self, "occupancy_hint", 0)),
-                             cta_order=int(getattr(self, "cta_order", 0)))
+                             cta_order=int(getattr(self, "cta_order", 0)), speculation=int(getattr(self, "speculation", 1)))
 
 
 class SingleLevelSampler(_Base):
@@ -101,12 +101,14 @@ class SingleLevelSampler(_Base):
     burn_rows    saved rows with index >= burn_rows accumulate the temperature-1 log-likelihood
     lanes        lanes cooperating on one chain (1, 2, 4; 0 = the library's choice for this chain count)
     co_resident_chains  chains of OTHER samplers whose launches run concurrently with this one (other streams);
-                 only used to choose `lanes`
+                 only used to choose `lanes` and `speculation`
+    speculation  depth of speculative evaluation (1 none, 2, 4, 8; 0 = the library's choice for this chain count):
+                 the latency form for launches with few chains; the chains are bit-identical for every depth
     """
 
     def __init__(self, model, pack, dataset_id, temperature, theta0, variant="fit", cov0=None, adapt_when=None,
                  seed=1, chain_id_base=0, thinning=5, burn_rows=NO_BURN, device=None, stage=True, block_threads=0,
-                 lanes=0, co_resident_chains=0):
+                 lanes=0, co_resident_chains=0, speculation=0):
         if model not in (1, 2):
             raise ValueError("model must be 1 or 2")
         assert isinstance(pack, SinglePack)
@@ -134,13 +136,19 @@ class SingleLevelSampler(_Base):
         L = _lib.load()
         if lanes not in (0, 1, 2, 4):
             raise ValueError("lanes must be 0, 1, 2 or 4")
+        if speculation not in (0, 1, 2, 4, 8):
+            raise ValueError("speculation must be 0, 1, 2, 4 or 8")
         with torch.cuda.device(self.device):
-            self.lanes = int(lanes) if lanes else int(L.phf_am_single_lanes(n + int(co_resident_chains)))
+            lo, so = C.c_int32(0), C.c_int32(0)
+            _lib.check(L.phf_am_single_shape(n + int(co_resident_chains), int(lanes), int(speculation), C.byref(lo),
+                                             C.byref(so)), "phf_am_single_shape")
+            self.lanes, self.speculation = int(lo.value), int(so.value)
         self.block_threads = block_threads
         self.stage_groups = 0
+        per_chain = self.lanes * self.speculation
         if stage and n > 0 and np.all(np.diff(ids) >= 0):
-            bt = block_threads if block_threads > 0 else self._default_block(n * self.lanes)
-            need = pack.stage_groups_needed(ids, bt // self.lanes)   # a CTA of bt threads covers bt/lanes chains
+            bt = block_threads if block_threads > 0 else (128 if self.speculation > 1 else self._default_block(n * per_chain))
+            need = pack.stage_groups_needed(ids, bt // per_chain)   # a CTA of bt threads covers bt/per_chain chains
             if need * 64 <= 96 * 1024:
                 self.stage_groups, self.block_threads = need, bt
         with torch.cuda.device(self.device):

@@ -38,7 +38,7 @@ def log_py_from_means(temps, means):
 
 
 def run_ti(datasets, models=(1, 2), temps=None, replicates=1, iterations=500000, thinning=5, burn_in_fraction=4,
-           seed=1, segment=50000, device=None, progress=None, lanes=0, pack=None):
+           seed=1, segment=50000, device=None, progress=None, lanes=0, pack=None, speculation=0):
     """datasets: list of (concs, responses).  Returns dict with log_py[model] -> [n_pairs], B12 [n_pairs],
     means[model] -> [n_pairs, T] (averaged over replicates), acceptance[model] -> [n_pairs, T, R].
     Under torch.distributed (one process per GPU) the global chain list is sharded contiguously over the ranks and
@@ -66,7 +66,7 @@ def run_ti(datasets, models=(1, 2), temps=None, replicates=1, iterations=500000,
             d = 2 if model == 1 else 3
             samplers[model] = SingleLevelSampler(model, pack, ids[lo:hi], tt[lo:hi], np.ones((hi - lo, d)),
                                                  variant="temp", seed=seed, chain_id_base=(model - 1) * (1 << 40) + lo,
-                                                 thinning=thinning, burn_rows=burn, device=dev, lanes=lanes,
+                                                 thinning=thinning, burn_rows=burn, device=dev, lanes=lanes, speculation=speculation,
                                                  co_resident_chains=(hi - lo) * (len(models) - 1))
             streams[model] = torch.cuda.Stream(device=dev)
         torch.cuda.synchronize(dev)
@@ -88,6 +88,7 @@ def run_ti(datasets, models=(1, 2), temps=None, replicates=1, iterations=500000,
         out["sample_seconds"] = time.perf_counter() - t_start   # this rank's sampling phase (launch to synchronise)
     out["chains_local"] = (hi - lo) * len(models)
     out["lanes"] = {m: samplers[m].lanes for m in samplers}
+    out["speculation"] = {m: samplers[m].speculation for m in samplers}
     t_gather = time.perf_counter()
     for model in models:
         d = 2 if model == 1 else 3

@@ -428,3 +428,66 @@ def test_cta_order_does_not_change_results(table, model, lanes):
     assert np.array_equal(a.state.cpu().numpy(), b.state.cpu().numpy())
     rr = a.run(200, row_major=True).cpu().numpy()          # the row-major layout goes through the same block index
     assert np.array_equal(rr.transpose(1, 0, 2), b.run(200).cpu().numpy())
+
+
+@pytest.mark.parametrize("model,variant,lanes,depth", [(2, "temp", 4, 4), (2, "fit", 2, 4), (1, "temp", 4, 2), (1, "fit", 1, 4),
+                                                       (2, "temp", 1, 2), (2, "fit", 4, 8), (1, "temp", 2, 8),
+                                                       (2, "temp", 2, 2)])
+def test_speculative_evaluation_gives_the_same_chain_bit_for_bit(table, model, variant, lanes, depth):
+    """cfg.speculation (csrc/phf_single_spec.cu): `depth` groups of `lanes` lanes evaluate the next `depth` proposals at
+    once under the hypothesis that their predecessors are rejected.  Every committed number is computed by the same
+    expressions from the same inputs as in the sequential loop, so samples, final state, acceptance counts and the
+    thermodynamic-integration accumulator are IDENTICAL to speculation = 1 with the same lane count -- across the start
+    of adaptation (and PyHillTemp's mean reset), ragged chain counts, launch boundaries that are not multiples of the
+    depth or the thinning, discarded burn-in rows and both sample layouts; and the chain follows the C oracle."""
+    from pyhillfit_b200.packing import SinglePack
+    from pyhillfit_b200.sampler import SingleLevelSampler, variant_defaults
+    pairs = [("Amiodarone", "hERG"), ("Bepridil", "hERG"), ("Amitriptyline", "Kv4.3"), ("Dofetilide", "hERG"),
+             ("Diltiazem", "Cav1.2")]
+    pack = SinglePack([table.concat(d, c) for d, c in pairs])
+    d = 2 if model == 1 else 3
+    n_per = 7                                     # 35 chains: ragged for every lanes x depth
+    ids = np.repeat(np.arange(len(pairs), dtype=np.int32), n_per)
+    rng = np.random.default_rng(11)
+    tt = rng.choice([1.0, 0.421875, 0.0, 0.015625], len(ids)) if variant == "temp" else np.ones(len(ids))
+    if variant == "temp":
+        theta0 = np.ones((len(ids), d))
+    else:
+        theta0 = np.stack([rng.uniform(4.5, 6.5, len(ids)), rng.uniform(0.6, 1.4, len(ids)),
+                           rng.uniform(4, 9, len(ids))], 1)
+        theta0 = theta0 if model == 2 else theta0[:, [0, 2]]
+    kw = dict(variant=variant, adapt_when=120, seed=5, chain_id_base=300, thinning=5, burn_rows=30, lanes=lanes)
+    segs = (7, 333, 160, 1, 99)                    # 600 iterations; boundaries off the thinning and the depth
+    runs = {}
+    for spec in (1, depth):
+        for layout in (False, True):
+            s = SingleLevelSampler(model, pack, ids, tt, theta0, speculation=spec, **kw)
+            assert s.speculation == spec and s.lanes == lanes
+            parts = []
+            for k in segs:
+                r = s.run(k, row_major=layout, discard_burn=layout)
+                parts.append((r.transpose(0, 1) if layout else r).cpu().numpy())
+            runs[(spec, layout)] = (np.concatenate(parts, axis=1), s.state.cpu().numpy(), s.loglik_t1_mean())
+    for layout in (False, True):
+        a, b = runs[(1, layout)], runs[(depth, layout)]
+        assert a[0].shape == b[0].shape == (len(ids), 120 if not layout else 120 - 29, d + 1)
+        assert np.array_equal(a[0], b[0]), "samples differ (layout %s)" % layout
+        assert np.array_equal(a[1], b[1]), "final state differs"
+        assert np.array_equal(a[2], b[2])
+    assert np.array_equal(runs[(depth, False)][0][:, 29:, :], runs[(depth, True)][0])
+    # and the chain is the oracle's
+    cov0, _, reset = variant_defaults(variant, theta0)
+    got = runs[(depth, False)][0]
+    for k in (0, 8, 20, 34):
+        concs, y = table.concat(*pairs[ids[k]])
+        want, st = _oracle_chain(model, concs, y, tt[k], theta0[k], cov0[k], 600, 5, 120, reset, 5, 300 + k)
+        assert np.allclose(got[k], want, rtol=1e-8, atol=1e-8), "chain %d diverged from the oracle" % k
+        assert runs[(depth, False)][1][k, -1] == st[-1]
+
+
+def test_speculation_is_chosen_for_small_launches_only(table):
+    from pyhillfit_b200 import _lib
+    L = _lib.load()
+    assert L.phf_am_single_speculation(4000000, 1) == 1       # throughput regime: no speculation
+    assert L.phf_am_single_speculation(26880, 2) == 1
+    assert L.phf_am_single_speculation(500, 4) >= 4           # a handful of chains: deep speculation
