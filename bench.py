@@ -300,8 +300,8 @@ def main():
     ap.add_argument("--chains-per-pair", type=int, default=64)
     ap.add_argument("--thinning", type=int, default=5)
     ap.add_argument("--ref-iters-per-step", type=int, default=4000)
-    ap.add_argument("--e2e-steps", type=int, default=6)
-    ap.add_argument("--e2e-segments", type=int, default=32)
+    ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--e2e-segments", type=int, default=64)
     ap.add_argument("--layout", default="row", choices=["row", "chain"],
                     help="sample layout of the device-timed step AND of the end-to-end call: row = [row][chain][d+1] "
                          "(coalesced write-out, contiguous transfers)")

@@ -100,6 +100,7 @@ struct ChainConst {
     double pi_bit, n_other_total, temp;
     uint32_t thinning, adapt_when, burn_rows, row_base;
     int reset_mean;
+    PrepView pv;        // this lane's prepared dose-group records (phf_single.cuh)
     double *out;        // this chain's first row in the samples buffer, or nullptr
     size_t row_stride;  // doubles between two rows of the chain
     bool active;
@@ -117,8 +118,8 @@ PHF_DI void am_step(const double *T, const ChainConst &cc, ChainRegs<MODEL> &s, 
 
     // ---- target, accept (PyHillFit.py:833-838) ----
     double lt_star, l1_star;
-    single_log_target_lanes<MODEL, G, true>(T, star, cc.grp, cc.ng, cc.pi_bit, cc.n_other_total, cc.temp, gl, mask,
-                                            lt_star, l1_star);
+    single_log_target_lanes<MODEL, G, true, true>(T, star, cc.grp, cc.ng, cc.pi_bit, cc.n_other_total, cc.temp, gl, mask,
+                                                  lt_star, l1_star, cc.pv);
     const bool accepted = dr.log_u < lt_star - s.lt;
     if (accepted) {
 #pragma unroll
@@ -311,7 +312,17 @@ __global__ void __launch_bounds__(128, MINB)
 
     // shared memory after the staged groups: [G > 1: one draw slot of D+1 doubles per thread][32 gamma_s per warp]
     double *const slots = reinterpret_cast<double *>(smem_raw + (size_t)cfg.stage_groups * sizeof(phf_dose_group));
-    double *const gam_slots = slots + (G > 1 ? (size_t)blockDim.x * (D + 1) : 0) + (size_t)(threadIdx.x & ~31u);
+    double *const gam_base = slots + (G > 1 ? (size_t)blockDim.x * (D + 1) : 0);
+    double *const gam_slots = gam_base + (size_t)(threadIdx.x & ~31u);
+    {   // this lane's prepared dose-group records (after the gamma slots; only this thread reads them)
+        constexpr int U = 4 / G;
+        double2 *const prep = reinterpret_cast<double2 *>(gam_base + blockDim.x) + threadIdx.x;
+        bool both = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            prepare_group<MODEL>(cc.grp, gl + u * G, cc.ng, prep + (size_t)(u * kPrepPairs) * blockDim.x, (int)blockDim.x, both);
+        cc.pv = PrepView{prep, (int)blockDim.x, both};
+    }
 
     // The draws of an iteration depend on t only: once every G iterations lane gl prepares the draws of iteration
     // t + gl and parks them in its shared-memory slot; each iteration then reads its slot (a broadcast load: 2
@@ -381,7 +392,7 @@ static int launch_am_single(const phf_am_config &cfg, int64_t n, int block, size
 {
     auto kern = am_single_kernel<MODEL, G, MINB>;
     cudaError_t e;
-    if (smem > 48 * 1024 &&
+    if (smem > 40 * 1024 &&  // (the 48 KB default limit counts the kernel's static shared memory too)
         (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)))
         return set_cuda_error(e, "cudaFuncSetAttribute");
     const int cta_chains = block / G;
@@ -534,10 +545,11 @@ extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, dou
     if (depth > 1)
         return am_single_spec_launch(*cfg, lanes, depth, n_chains, block, state, dataset_id, temperature, datasets, groups,
                                      samples, (cudaStream_t)stream);
-    // staged dose groups + (lanes > 1) one draw slot of d+1 doubles per thread + 32 gamma_s per warp
+    // staged dose groups + (lanes > 1) one draw slot of d+1 doubles per thread + 32 gamma_s per warp + 4 / lanes
+    // prepared dose-group records of 64 bytes per thread
     const size_t smem = (size_t)cfg->stage_groups * sizeof(phf_dose_group) +
                         (lanes > 1 ? (size_t)block * ((cfg->model == 1 ? 2 : 3) + 1) * sizeof(double) : 0) +
-                        (size_t)block * sizeof(double);
+                        (size_t)block * sizeof(double) + (size_t)block * (4 / lanes) * 64;
     if (smem > 200 * 1024) return set_error(PHF_EINVAL, "cfg.stage_groups needs more than 200 KB of shared memory");
     cudaStream_t s = (cudaStream_t)stream;
     const int minb = cfg->min_ctas_hint > 0 ? cfg->min_ctas_hint : 3;  // 168 registers: no spills; measured best at every size

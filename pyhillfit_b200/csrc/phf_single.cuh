@@ -61,6 +61,52 @@ PHF_DI double censored_pair(const double *T, double z0, double w0, double z1, do
     return acc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Prepared dose-group records (sampler kernels).  The U = 4/G dose groups a lane evaluates in its straight-line block
+// never change during a launch, and neither does what the per-iteration code used to work out about them: is the
+// group there at all (a lane past the dataset's last dose), does it carry zeros or hundreds, which of (0 - p) and
+// (p - 100) feeds log Phi and with what weight.  Each lane therefore resolves its U groups ONCE, in the kernel's
+// prologue, into records in shared memory -- 8 doubles: (ln dose hi | dose, ln dose lo, ybar, n_other, ss, csign,
+// coff, cw) with z = fma(csign, p, coff) / sigma = (0 - p) / sigma for zeros (csign -1, coff 0) or (p - 100) / sigma
+// for hundreds (csign +1, coff -100), bit for bit the old expressions; an absent group is the all-zero record with
+// csign +1, coff -100 (its Gaussian term is exactly 0, its weight 0).  The iteration then runs 4 LDS.128 per dose
+// from a known address space (the unprepared path reads the groups through a pointer that may be shared OR global:
+// generic LD.E loads) and none of the compares / selects.  Layout: double2 [u][pair][thread] -- a quarter-warp's
+// 16-byte loads are consecutive, conflict-free.  A dose carrying zeros AND hundreds (none in the Crumb table) keeps
+// its second term on the rare path below, which reads the raw groups.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPrepPairs = 4;  // double2 per record
+
+template <int MODEL>
+PHF_DI void prepare_group(const phf_dose_group *__restrict__ grp, int g, int ng, double2 *dst, int stride, bool &both)
+{
+    double a0 = 0.0, a1 = 0.0, ybar = 0.0, n_other = 0.0, ss = 0.0, csign = 1.0, coff = -100.0, cw = 0.0;
+    if (g < ng) {
+        const phf_dose_group Gd = grp[g];
+        a0 = MODEL == 2 ? Gd.lnc_hi : Gd.conc;
+        a1 = Gd.lnc_lo;
+        ybar = Gd.ybar;
+        n_other = Gd.n_other;
+        ss = Gd.ss;
+        const bool has0 = Gd.n0 > 0.0, has100 = Gd.n100 > 0.0;
+        csign = has0 ? -1.0 : 1.0;
+        coff = has0 ? 0.0 : -100.0;
+        cw = has0 ? Gd.n0 : (has100 ? Gd.n100 : 0.0);
+        both = both || (has0 && has100);
+    }
+    dst[0 * stride] = make_double2(a0, a1);
+    dst[1 * stride] = make_double2(ybar, n_other);
+    dst[2 * stride] = make_double2(ss, csign);
+    dst[3 * stride] = make_double2(coff, cw);
+}
+
+// what a sampler kernel hands to single_log_target_lanes when its lanes' records are prepared
+struct PrepView {
+    const double2 *rec;  // this thread's first double2 (record u, pair q at rec[(u * kPrepPairs + q) * stride])
+    int stride;          // threads per CTA
+    bool both_kinds;     // some dose of this lane carries zeros and hundreds
+};
+
 // Evaluate t * loglik + logprior and the temperature-1 loglik for one parameter vector with G cooperating
 // lanes (G = 1: a single thread).  Every lane of the group passes the same th; lane gl evaluates dose groups
 // gl, gl+G, ...; lanes 0 and 1 evaluate the two logarithms of sigma; sums are butterfly reductions, so every
@@ -79,10 +125,10 @@ PHF_DI double censored_pair(const double *T, double z0, double w0, double z1, do
 // G >= 2: there is ONE shuffle point (ptxas ends a basic block with a convergence check at every shuffle point, and
 // nothing is scheduled across it).  Lane 0 folds -n_other ln(sigma) - pi_bit into its partial of the likelihood sum,
 // lane 1 carries 4 ln(sigma - 1e-3) in the prior sum, so the two logarithms need no exchange of their own.
-template <int MODEL, int G, bool VOTE>
+template <int MODEL, int G, bool VOTE, bool PREP = false>
 PHF_DI void single_log_target_lanes(const double *T, const double *th, const phf_dose_group *__restrict__ grp, int ng,
                                     double pi_bit, double n_other_total, double temperature, int gl, unsigned mask,
-                                    double &log_target, double &loglik_t1)
+                                    double &log_target, double &loglik_t1, const PrepView pv = PrepView{nullptr, 0, false})
 {
     const double pic50 = th[0];
     const double hill = MODEL == 2 ? th[1] : 1.0;
@@ -114,6 +160,19 @@ PHF_DI void single_log_target_lanes(const double *T, const double *th, const phf
     bool both_kinds = false;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+        if (PREP) {
+            // prepared record (see prepare_group): no presence / censoring logic left in the iteration
+            const double2 r0 = pv.rec[(u * kPrepPairs + 0) * pv.stride], r1 = pv.rec[(u * kPrepPairs + 1) * pv.stride];
+            const double2 r2 = pv.rec[(u * kPrepPairs + 2) * pv.stride], r3 = pv.rec[(u * kPrepPairs + 3) * pv.stride];
+            const double x = MODEL == 2 ? hill_ratio_pow<!VOTE>(T, r0.x, r0.y, lic_hi, lic_lo, hill) : r0.x * inv_ic50;
+            const double p = hill_response(x);
+            const double r = r1.x - p;
+            e2 += fma(r1.y * r, r, r2.x);
+            zc[u] = fma(r2.y, p, r3.x) * inv_s;  // (0 - p) / sigma or (p - 100) / sigma: doseresponse.py:218-219, 244-245
+            wc[u] = r3.y;
+            pu[u] = p;
+            continue;
+        }
         const int g = gl + u * G;
         const bool on = g < ng;
         const phf_dose_group *Gp = grp + (on ? g : 0);
@@ -138,7 +197,7 @@ PHF_DI void single_log_target_lanes(const double *T, const double *th, const phf
 #pragma unroll
         for (int u = 0; u + 1 < U; u += 2) cens += censored_pair<VOTE, PW>(T, zc[u], wc[u], zc[u + 1], wc[u + 1]);
     }
-    if (both_kinds) {  // a dose carrying zeros AND hundreds (none in the Crumb table): its second term
+    if (PREP ? pv.both_kinds : both_kinds) {  // a dose carrying zeros AND hundreds (none in the Crumb table): its second term
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int g = gl + u * G;

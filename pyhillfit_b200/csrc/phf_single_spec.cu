@@ -132,6 +132,19 @@ __global__ void __launch_bounds__(128, 3)
     double *const ring = reinterpret_cast<double *>(smem_raw + (size_t)cfg.stage_groups * sizeof(phf_dose_group)) +
                          (size_t)(threadIdx.x / G) * (R * W);
     uint32_t filled = t;  // iterations (t, filled] are prepared
+    // this lane's prepared dose-group records (phf_single.cuh), after the rings; only this thread reads them
+    PrepView pv;
+    {
+        constexpr int U = 4 / E;
+        double2 *const prep = reinterpret_cast<double2 *>(
+                                  reinterpret_cast<double *>(smem_raw + (size_t)cfg.stage_groups * sizeof(phf_dose_group)) +
+                                  (size_t)cta_chains * (R * W)) + threadIdx.x;
+        bool both = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            prepare_group<MODEL>(grp, el + u * E, ng, prep + (size_t)(u * kPrepPairs) * blockDim.x, (int)blockDim.x, both);
+        pv = PrepView{prep, (int)blockDim.x, both};
+    }
 
     for (;;) {
         const bool alive = t < t_end;
@@ -190,7 +203,8 @@ __global__ void __launch_bounds__(128, 3)
         double star[D];
         propose<MODEL>(T, s.th, h_cov, h_loga, z, star);
         double lt_star, l1_star;
-        single_log_target_lanes<MODEL, E, true>(T, star, grp, ng, pi_bit, n_other_total, temp, el, full, lt_star, l1_star);
+        single_log_target_lanes<MODEL, E, true, true>(T, star, grp, ng, pi_bit, n_other_total, temp, el, full, lt_star,
+                                                      l1_star, pv);
 
         // ---- resolve: the first accepted group ends the round ----
         const uint32_t left = alive ? t_end - t : 0u;
@@ -287,10 +301,10 @@ static int launch_spec(const phf_am_config &cfg, int64_t n, int block, double *s
     auto kern = am_single_spec_kernel<MODEL, E, S>;
     const int cta_chains = block / G;
     const size_t smem = (size_t)cfg.stage_groups * sizeof(phf_dose_group) +
-                        (size_t)cta_chains * (2 * G) * (D + 2) * sizeof(double);
+                        (size_t)cta_chains * (2 * G) * (D + 2) * sizeof(double) + (size_t)block * (4 / E) * 64;
     cudaError_t e;
     if (smem > 200 * 1024) return set_error(PHF_EINVAL, "cfg.stage_groups needs more than 200 KB of shared memory");
-    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)))
+    if (smem > 40 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)))
         return set_cuda_error(e, "cudaFuncSetAttribute");
     const unsigned grid = (unsigned)((n + cta_chains - 1) / cta_chains);
     kern<<<grid, block, smem, s>>>(cfg, n, state, dataset_id, temperature, datasets, groups, samples);
