@@ -206,7 +206,7 @@ int phf_hier_log_target_batch(int64_t n, const double *theta, int32_t theta_stri
 /* All chains of one call share n_expts (so dim); state rows are PHF_STATE_SIZE(dim) doubles.
  * n_expts <= PHF_HIER_MAX_EXPTS: lane-per-parameter kernels (16 or 32 lanes per chain: the latency form), or, with
  * cfg->lanes_per_chain = 1 and n_expts <= 6, one thread per chain (the throughput form: twice the rate of the lane
- * kernel for tens of thousands of chains; cfg->lanes_per_chain = 0 picks it for n_expts <= 3 and >= 80 chains per
+ * kernel for tens of thousands of chains; cfg->lanes_per_chain = 0 picks it for n_expts <= 4 and >= 64 chains per
  * SM); up to PHF_HIER_BIG_MAX_EXPTS: warp-per-chain kernel (takes a stream-ordered temporary of
  * n_chains * dim (dim+1) / 2 doubles for the Cholesky factors).  The kernels run the same algorithm on the same
  * Philox stream and agree to rounding (the log-target's summation order differs).

@@ -435,12 +435,15 @@ static int launch_am_hier(const phf_am_config &cfg, int64_t n, double *state, co
 
 // phf_hier_thread.cu: one thread per chain, n_expts <= kHierThreadMaxExpts
 constexpr int kHierThreadMaxExpts = 6;
-// cfg.lanes_per_chain == 0 picks the thread kernel for at most 3 experiments (its Cholesky factor fits in registers and
-// 9-11 warps share an SM) once the launch has 80 chains per SM: measured on B200 (scripts/hier_probe.py, Ne = 3,
-// ms per 1000 iterations, lane kernel vs thread kernel): 9 856 chains 11.3 vs 11.4, 19 712: 20.0 vs 14.4,
-// 39 424: 38.8 vs 19.2; with 4 experiments the two kernels tie at 10 496 chains (12.6 vs 12.4).
-constexpr int kHierThreadAutoMaxExpts = 3;
-constexpr int kHierThreadMinChainsPerSm = 80;
+// cfg.lanes_per_chain == 0 picks the thread kernel for at most 4 experiments once the launch has 64 chains per SM:
+// measured on B200 (scripts/hier_probe.py, ms per 1000 iterations, lane kernel vs thread kernel): Ne = 3, 9 856 chains
+// 11.3 vs 11.4, 19 712: 20.0 vs 14.4, 39 424: 38.8 vs 16.0; Ne = 4, 10 496 chains: 12.0 vs 12.2 alone -- a tie -- but
+// next to the Ne = 3 launch (BASELINE config 3 runs its four launches on four streams) the thread form's 328 warps fit
+// beside the Ne = 3 CTAs where the lane form's 5 248 warps queue behind them: 30.8 against 33.5 ms for the whole
+// configuration (scripts/config3_probe.py, profiles/r02_config3_probe.txt).  Five and six experiments (3 072 and 768
+// chains) stay with the lane kernel: 5.0 / 4.0 ms against 14.9 / 15.0 (a lone warp's iteration is ~25 000 cycles).
+constexpr int kHierThreadAutoMaxExpts = 4;
+constexpr int kHierThreadMinChainsPerSm = 64;
 int am_hier_thread_launch(const phf_am_config &cfg, int32_t n_expts, int64_t n, double *state, const int32_t *dataset_id,
                           const phf_hier_dataset *datasets, const phf_hier_point *points, const phf_hier_priors &pr,
                           double *samples, cudaStream_t s);
