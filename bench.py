@@ -302,6 +302,8 @@ def main():
     ap.add_argument("--ref-iters-per-step", type=int, default=4000)
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--e2e-segments", type=int, default=64)
+    ap.add_argument("--e2e-threads-per-model", type=int, default=2,
+                    help="host threads making complete runs of one model concurrently (the library holds two workspaces per model)")
     ap.add_argument("--layout", default="row", choices=["row", "chain"],
                     help="sample layout of the device-timed step AND of the end-to-end call: row = [row][chain][d+1] "
                          "(coalesced write-out, contiguous transfers)")
@@ -779,9 +781,10 @@ def run_e2e(cx, state0):
     one complete PyHillFit run of `--iters-per-step` iterations of every chain: start state and packed data copied in
     (H2D), K iterations, the rows the reference SAVES copied back -- it drops the first quarter of the saved rows
     before np.savetxt (python/PyHillFit.py:861-864), so those are neither written nor transferred
-    (cfg.discard_burn_rows) -- plus the final state (D2H).  The two models are driven by two host threads, each making
-    its `--e2e-steps` calls back to back (a call returns when its results are on the host), so one model's transfers
-    overlap the other's burn-in phase; the timed region is the wall clock from the barrier to the last call's return."""
+    (cfg.discard_burn_rows) -- plus the final state (D2H).  Each model is driven by `--e2e-threads-per-model` host threads
+    (the library keeps two workspaces per model), each making its share of the `--e2e-steps` runs back to back (a call
+    returns when its results are on the host), so one run's transfers fall into another's burn-in phase, when a run has
+    nothing to copy; the timed region is the wall clock from the barrier to the last call's return."""
     import ctypes as C
     from pyhillfit_b200 import _lib
     args, torch, dev, pack, wl, rank, world = cx.args, cx.torch, cx.dev, cx.pack, cx.wl, cx.rank, cx.world
@@ -793,21 +796,23 @@ def run_e2e(cx, state0):
     row_major = args.layout == "row"
     jobs = {}
     h2d = d2h = 0
+    T = args.e2e_threads_per_model
     for model in (1, 2):
         w = wl[model]
         n, d = len(w["ids"]), w["d"]
         st0 = state0[model].pin_memory()
-        st = torch.empty_like(st0).pin_memory()
-        # row-major samples: [row][chain][d+1], every segment is one contiguous device -> host transfer
-        smp = torch.empty((rows, n, d + 1) if row_major else (n, rows, d + 1), dtype=torch.float64).pin_memory()
         ids = np.ascontiguousarray(w["ids"])
         temps = np.ones(n)
-        jobs[model] = dict(n=n, state0=st0, state=st, samples=smp, ids=ids, temps=temps)
+        for k in range(T):      # every host thread owns its result buffers
+            st = torch.empty_like(st0).pin_memory()
+            # row-major samples: [row][chain][d+1], every segment is one contiguous device -> host transfer
+            smp = torch.empty((rows, n, d + 1) if row_major else (n, rows, d + 1), dtype=torch.float64).pin_memory()
+            jobs[(model, k)] = dict(n=n, state0=st0, state=st, samples=smp, ids=ids, temps=temps)
         h2d += st.numel() * 8 + ids.nbytes + temps.nbytes + pack.datasets.nbytes + pack.groups.nbytes
         d2h += smp.numel() * 8 + st.numel() * 8
 
-    def call(model):
-        j = jobs[model]
+    def call(model, k):
+        j = jobs[(model, k)]
         j["state"].copy_(j["state0"])       # a complete run starts from the start state (host copy, inside the timed region)
         cfg = _lib.AmConfig(model=model, reset_mean_at_adapt=0, t0=0, n_iters=K, thinning=thin,
                             adapt_when=1000 * wl[model]["d"], burn_rows=burn, discard_burn_rows=1, rows_capacity=rows,
@@ -824,13 +829,13 @@ def run_e2e(cx, state0):
     def run(steps):
         errs = []
 
-        def loop(model):
+        def loop(model, k):
             try:
-                for _ in range(steps):
-                    call(model)
+                for _ in range(steps // T):
+                    call(model, k)
             except Exception as e:      # surface a failure of a worker thread
                 errs.append(e)
-        th = [threading.Thread(target=loop, args=(m,)) for m in (1, 2)]
+        th = [threading.Thread(target=loop, args=(m, k)) for m in (1, 2) for k in range(T)]
         for t in th:
             t.start()
         for t in th:
@@ -838,20 +843,21 @@ def run_e2e(cx, state0):
         if errs:
             raise errs[0]
 
-    run(2)
+    assert args.e2e_steps % T == 0
+    run(2 * T)
     cx.barrier()
     t0 = time.perf_counter()
     run(args.e2e_steps)
     torch.cuda.synchronize(dev)
     dt = cx.max_over_ranks(time.perf_counter() - t0)
-    total = float(sum(j["n"] for j in jobs.values())) * K * args.e2e_steps * world
+    total = float(sum(len(wl[m]["ids"]) for m in (1, 2))) * K * args.e2e_steps * world
     finite = bool(all(np.isfinite(j["samples"][-1].numpy()).all() for j in jobs.values()))
     return {"value": total / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": args.e2e_steps, "rows_kept_per_chain": rows, "rows_discarded_as_burn_in": burn - 1,
             "last_row_finite": finite,
             "api": "phf_am_single_run_host (pinned host buffers, %s-major samples, %d overlapped segments/call, "
-                   "cfg.discard_burn_rows = 1: the burn-in rows PyHillFit.py:861-864 drops are not transferred; one host "
-                   "thread per model, calls back to back)" % (args.layout, args.e2e_segments),
+                   "cfg.discard_burn_rows = 1: the burn-in rows PyHillFit.py:861-864 drops are not transferred; %d host "
+                   "thread(s) per model, each making its calls back to back)" % (args.layout, args.e2e_segments, T),
             "timing": "host wall clock from the barrier to the return of the last call (each call ends with a stream "
                       "synchronise); max over ranks"}
 

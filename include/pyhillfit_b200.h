@@ -250,9 +250,10 @@ int phf_am_single_run_host(const phf_am_config *cfg, int64_t n_chains, double *s
                            int32_t n_groups, const phf_dose_group *groups, double *samples, int32_t n_segments,
                            int32_t device);
 
-/* Thread safety of the *_host entry points: each call locks the workspace (device buffers, two streams, events) of its
- * (device, model) or (device, n_expts) pair for its whole duration, so calls for different pairs run concurrently
- * (bench.py drives models 1 and 2 from two host threads) and calls for the same pair serialise.
+/* Thread safety of the *_host entry points: each call holds one of the TWO workspaces (device buffers, two streams,
+ * events) of its (device, model) or (device, n_expts) pair for its whole duration, so calls for different pairs run
+ * concurrently, up to two calls for the same pair do too (bench.py drives each model from two host threads, so that one
+ * run's transfers fall into the other's burn-in phase), and further calls for that pair wait.
  * phf_release_workspaces() frees every workspace of every device (buffers, streams, events); later calls re-create
  * what they need.  Returns PHF_OK or the first CUDA error. */
 int phf_release_workspaces(void);

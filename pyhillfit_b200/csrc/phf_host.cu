@@ -46,19 +46,32 @@ struct Workspace {
     int device = 0;
 };
 
-// key: (device, 0 = single-level | 1 = hierarchical, model or n_expts)
+// key: (device, 0 = single-level | 1 = hierarchical, model or n_expts, slot).  kSlots workspaces per key: that many
+// calls for the same (device, model) run concurrently (two host threads each making complete runs keep the PCIe link
+// busy during each other's burn-in phase, when a run has nothing to copy back); further calls wait for a slot.
+constexpr int kSlots = 2;
 std::mutex g_registry_lock;
-std::map<std::tuple<int, int, int>, std::unique_ptr<Workspace>> g_registry;
+std::map<std::tuple<int, int, int, int>, std::unique_ptr<Workspace>> g_registry;
 
-Workspace &workspace_for(int device, int kind, int key)
+// Returns a LOCKED workspace (the caller adopts the lock): the first free slot, else it waits for slot 0.
+Workspace &acquire_workspace(int device, int kind, int key)
 {
-    std::lock_guard<std::mutex> g(g_registry_lock);
-    auto &slot = g_registry[std::make_tuple(device, kind, key)];
-    if (!slot) {
-        slot.reset(new Workspace);
-        slot->device = device;
+    Workspace *slots[kSlots];
+    {
+        std::lock_guard<std::mutex> g(g_registry_lock);
+        for (int i = 0; i < kSlots; ++i) {
+            auto &slot = g_registry[std::make_tuple(device, kind, key, i)];
+            if (!slot) {
+                slot.reset(new Workspace);
+                slot->device = device;
+            }
+            slots[i] = slot.get();
+        }
     }
-    return *slot;
+    for (int i = 0; i < kSlots; ++i)
+        if (slots[i]->lock.try_lock()) return *slots[i];
+    slots[0]->lock.lock();
+    return *slots[0];
 }
 
 // The entry points run on `device` and leave the calling thread's current device as they found it.
@@ -229,8 +242,8 @@ extern "C" int phf_am_single_run_host(const phf_am_config *cfg, int64_t n_chains
         return set_error(PHF_EINVAL, "cfg.rows_capacity is smaller than the rows this call produces");
     DeviceGuard guard;
     PHF_TRY(guard.enter(device), "cudaSetDevice");
-    Workspace &w = workspace_for(device, 0, cfg->model);
-    std::lock_guard<std::mutex> hold(w.lock);
+    Workspace &w = acquire_workspace(device, 0, cfg->model);
+    std::lock_guard<std::mutex> hold(w.lock, std::adopt_lock);
     if (int rc = ensure_streams(w)) return rc;
 
     PHF_TRY(w.state.ensure((size_t)n_chains * nf * sizeof(double)), "cudaMalloc");
@@ -285,8 +298,8 @@ extern "C" int phf_am_hier_run_host(const phf_am_config *cfg, int32_t n_expts, i
         return set_error(PHF_EINVAL, "cfg.rows_capacity is smaller than the rows this call produces");
     DeviceGuard guard;
     PHF_TRY(guard.enter(device), "cudaSetDevice");
-    Workspace &w = workspace_for(device, 1, n_expts);
-    std::lock_guard<std::mutex> hold(w.lock);
+    Workspace &w = acquire_workspace(device, 1, n_expts);
+    std::lock_guard<std::mutex> hold(w.lock, std::adopt_lock);
     if (int rc = ensure_streams(w)) return rc;
 
     // (w.datasets / w.groups hold the hierarchical datasets / points here)

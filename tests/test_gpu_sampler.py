@@ -491,3 +491,67 @@ def test_speculation_is_chosen_for_small_launches_only(table):
     assert L.phf_am_single_speculation(4000000, 1) == 1       # throughput regime: no speculation
     assert L.phf_am_single_speculation(26880, 2) == 1
     assert L.phf_am_single_speculation(500, 4) >= 4           # a handful of chains: deep speculation
+
+
+def test_host_entry_point_concurrent_calls_discarded_burn_in_and_release(table):
+    """Four host threads call phf_am_single_run_host for the SAME model at once (two workspaces per (device, model):
+    two run concurrently, two wait), with cfg.discard_burn_rows = 1: every call returns exactly the post-burn rows of
+    the device-pointer path; phf_release_workspaces() frees everything and the next call re-creates what it needs."""
+    import threading
+    import torch
+    from pyhillfit_b200 import _lib
+    from pyhillfit_b200.packing import SinglePack
+    from pyhillfit_b200.sampler import SingleLevelSampler
+    pack = SinglePack([table.concat(d, c) for d, c in table.pairs()[:16]])
+    ids = np.repeat(np.arange(16, dtype=np.int32), 8)
+    theta0 = np.tile([5.5, 1.0, 6.0], (len(ids), 1))
+    iters, thin = 1000, 5
+    saved = iters // thin + 1
+    burn = saved // 4
+    kw = dict(variant="fit", adapt_when=200, seed=11, thinning=thin, burn_rows=burn)
+    ref = SingleLevelSampler(2, pack, ids, 1.0, theta0, **kw)
+    state0 = ref.state.cpu().numpy().copy()
+    full = ref.run(iters).cpu().numpy()
+    want = full[:, burn - 1:, :]                      # rows burn .. saved-1 (PyHillFit.py:861-864)
+    kept = saved - burn
+    assert want.shape[1] == kept
+    L = _lib.load()
+    temps = np.ones(len(ids))
+    out, errs = {}, []
+
+    def worker(k, nseg):
+        try:
+            state = torch.from_numpy(state0.copy()).pin_memory().numpy()
+            samples = torch.zeros((kept, len(ids), 4), dtype=torch.float64).pin_memory().numpy()
+            cfg = _lib.AmConfig(model=2, reset_mean_at_adapt=0, t0=0, n_iters=iters, thinning=thin, adapt_when=200,
+                                burn_rows=burn, discard_burn_rows=1, rows_capacity=kept, seed=11, chain_id_base=0,
+                                lanes_per_chain=ref.lanes, speculation=ref.speculation,
+                                sample_layout=_lib.SAMPLES_ROW_MAJOR)
+            _lib.check(L.phf_am_single_run_host(C.byref(cfg), len(ids), state.ctypes.data, ids.ctypes.data,
+                                                temps.ctypes.data, pack.n_datasets, pack.datasets.ctypes.data,
+                                                len(pack.groups), pack.groups.ctypes.data, samples.ctypes.data, nseg, 0),
+                       "phf_am_single_run_host")
+            out[k] = (samples.transpose(1, 0, 2).copy(), state.copy())
+        except Exception as e:
+            errs.append(e)
+
+    threads = [threading.Thread(target=worker, args=(k, nseg)) for k, nseg in enumerate((1, 3, 8, 40))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    for k in range(4):
+        assert np.array_equal(out[k][0], want), k
+        assert np.array_equal(out[k][1], ref.state.cpu().numpy()), k
+    assert L.phf_release_workspaces() == 0
+    worker(9, 5)
+    assert not errs and np.array_equal(out[9][0], want)
+    # a capacity that ignores the discarded rows is accepted, one below the kept rows is refused
+    cfg = _lib.AmConfig(model=2, t0=0, n_iters=iters, thinning=thin, adapt_when=200, burn_rows=burn, discard_burn_rows=1,
+                        rows_capacity=kept - 1, seed=11)
+    st = state0.copy()
+    buf = np.zeros((kept, len(ids), 4))
+    assert L.phf_am_single_run_host(C.byref(cfg), len(ids), st.ctypes.data, ids.ctypes.data, temps.ctypes.data,
+                                    pack.n_datasets, pack.datasets.ctypes.data, len(pack.groups),
+                                    pack.groups.ctypes.data, buf.ctypes.data, 4, 0) == -1
