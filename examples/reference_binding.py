@@ -27,7 +27,8 @@ class AmConfig(C.Structure):                                                    
                 ("thinning", C.c_uint32), ("adapt_when", C.c_uint32), ("burn_rows", C.c_uint32),
                 ("rows_capacity", C.c_uint32), ("seed", C.c_uint64), ("chain_id_base", C.c_uint64),
                 ("stage_groups", C.c_int32), ("block_threads", C.c_int32), ("lanes_per_chain", C.c_int32),
-                ("min_ctas_hint", C.c_int32), ("sample_layout", C.c_int32), ("cta_order", C.c_int32)]
+                ("min_ctas_hint", C.c_int32), ("sample_layout", C.c_int32), ("cta_order", C.c_int32),
+                ("discard_burn_rows", C.c_int32), ("speculation", C.c_int32)]
 
 
 def _check(rc):
