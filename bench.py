@@ -268,7 +268,8 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": DATA,
-            "config": {"workload": WORKLOAD % (args.chains_per_pair, 5), "sample": sample},
+            "config": {"workload": WORKLOAD % (args.chains_per_pair, 5), "chains_per_pair": args.chains_per_pair, "thinning": 5},
+            "config_detail": {"sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "ess_per_s": float(np.mean(ess))},
             "ess_per_s": float(np.mean(ess)),
@@ -558,13 +559,14 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": DATA,
-            "config": {"workload": WORKLOAD % (args.chains_per_pair, thin), "chains_per_gpu": n_chains,
-                       "iters_per_step": K, "sample_layout": args.layout + "-major (value and e2e alike)",
-                       "theta0": "host least-squares fit; chains 1..63 of a pair jittered by 2%",
-                       "l2": "each step writes %.2f GB of thinned samples (> 126 MB L2); chain state is register-"
-                             "resident, packed data (54 KB) is staged in shared memory" %
-                             (n_chains * K * bytes_iter / 1e9),
-                       "target_1e10_frac": value / world / 1e10},
+            "config": {"workload": WORKLOAD % (args.chains_per_pair, thin), "chains_per_pair": args.chains_per_pair, "thinning": thin,
+                       "l2": "no flush needed: each step writes %.2f GB of thinned samples (> 126 MB L2); chain state is "
+                             "register-resident, packed data (54 KB) is staged in shared memory" %
+                             (n_chains * K * bytes_iter / 1e9)},
+            "config_detail": {"chains_per_gpu": n_chains,
+                              "iters_per_step": K, "sample_layout": args.layout + "-major (value and e2e alike)",
+                              "theta0": "host least-squares fit; chains 1..63 of a pair jittered by 2%",
+                              "target_1e10_frac": value / world / 1e10},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk, "ess_per_s": ess_per_s, "mean_acceptance": acc,
             "hbm_bytes_per_chain_iteration": bytes_iter, "flops_per_chain_iteration": flops_iter,

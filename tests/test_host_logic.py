@@ -328,3 +328,19 @@ def test_from_uniform_packer_equals_scalar_packer():
     assert len(fast.groups) == len(slow.groups)
     for f in fast.groups.dtype.names:
         assert np.array_equal(fast.groups[f], slow.groups[f]), f
+
+
+def test_dataset_cost_orders_datasets_by_work():
+    """SinglePack.dataset_cost (the weight ranks are balanced by): more unique doses and more censored doses cost more;
+    model 1 is cheaper than model 2; the cumulative-sum bookkeeping survives datasets without any censored dose."""
+    from pyhillfit_b200.packing import SinglePack
+    c4 = np.array([0.1, 1.0, 10.0, 100.0])
+    plain = (np.tile(c4, 3), np.tile([10.0, 30.0, 60.0, 90.0], 3))
+    zeros = (np.tile(c4, 3), np.tile([0.0, 30.0, 60.0, 90.0], 3))
+    both = (np.tile(c4, 3), np.tile([0.0, 30.0, 60.0, 100.0], 3))
+    two = (np.tile(c4[:2], 3), np.tile([10.0, 30.0], 3))
+    pack = SinglePack([plain, zeros, both, two, plain])
+    c = pack.dataset_cost(2)
+    assert c[0] == c[4] and c[1] > c[0] and c[2] > c[1] and c[3] < c[0]
+    assert c[1] - c[0] == pytest.approx(133.0) and c[2] - c[0] == pytest.approx(266.0)
+    assert np.all(pack.dataset_cost(1) < c)
