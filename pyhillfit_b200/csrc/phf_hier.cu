@@ -425,7 +425,10 @@ static int launch_am_hier(const phf_am_config &cfg, int64_t n, double *state, co
                           const phf_hier_dataset *datasets, const phf_hier_point *points, const phf_hier_priors &pr,
                           double *samples, cudaStream_t s)
 {
-    const int block = 128;  // 4 warps; G lanes per chain
+    // 4 warps per CTA by default; cfg.block_threads = 32 / 64 / 96 gives smaller CTAs, which find room on an SM next to
+    // the large CTAs of a concurrently running thread-per-chain launch (BASELINE config 3: see kHierLaneSmallCtaChains)
+    int block = cfg.block_threads > 0 ? cfg.block_threads : 128;
+    if (block % 32 != 0 || block > 128) return set_error(PHF_EINVAL, "cfg.block_threads must be a multiple of 32, at most 128");
     const int64_t lanes = n * G;
     const unsigned grid = (unsigned)((lanes + block - 1) / block);
     am_hier_kernel<G, DIM><<<grid, block, 0, s>>>(cfg, n, state, dataset_id, datasets, points, pr, samples);

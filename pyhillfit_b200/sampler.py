@@ -214,7 +214,7 @@ class HierarchicalSampler(_Base):
     """n independent chains of the hierarchical model; every chain's dataset has `n_expts` experiments."""
 
     def __init__(self, pack, dataset_id, theta0, priors, cov0=None, adapt_when=None, seed=1, chain_id_base=0,
-                 thinning=5, device=None, lanes=0):
+                 thinning=5, device=None, lanes=0, block_threads=0):
         """lanes: 1 = one thread per chain (throughput form, at most 6 experiments), 16 / 32 = one lane per parameter
         row (latency form), 0 = the library picks from the chain count."""
         assert isinstance(pack, HierPack)
@@ -236,7 +236,7 @@ class HierarchicalSampler(_Base):
         self.adapt_when = dwhen if adapt_when is None else adapt_when
         self.reset_mean = False
         self.seed, self.chain_id_base, self.thinning = seed, chain_id_base, int(thinning)
-        self.burn_rows, self.stage_groups, self.block_threads = NO_BURN, 0, 0
+        self.burn_rows, self.stage_groups, self.block_threads = NO_BURN, 0, int(block_threads)
         self.pack, self.priors = pack, priors
         self._alloc_common(n, theta0, cov0, device)
         torch = self.torch

@@ -26,8 +26,9 @@ def build(choice):
         hp = HierPack([table.experiments(*pairs[i]) for i in idxs])
         hid = np.repeat(np.arange(len(idxs), dtype=np.int32), 256)
         th0 = np.tile(np.concatenate(([1.0, 4.0, 6.0, 0.3], np.tile([5.5, 1.0], ne), [8.0])), (len(hid), 1))
-        lanes, hint = choice[ne]
-        hs = HierarchicalSampler(hp, hid, th0, pr, seed=ne, thinning=5, lanes=lanes)
+        lanes, hint = choice[ne][:2]
+        hs = HierarchicalSampler(hp, hid, th0, pr, seed=ne, thinning=5, lanes=lanes,
+                                 block_threads=choice[ne][2] if len(choice[ne]) > 2 else 0)
         hs.occupancy_hint = hint
         hb = torch.empty((hs.n, K // 5, hs.d + 1), dtype=torch.float64, device="cuda")
         out.append((hs, hb, torch.cuda.Stream()))
@@ -47,6 +48,9 @@ def timed(fn, reps=3):
 choices = {
     "round-1 default (Ne=3 thread/smem, others lane)": {3: (1, 1), 4: (16, 0), 5: (16, 0), 6: (32, 0)},
     "Ne=3,4 thread, 5,6 lane": {3: (1, 1), 4: (1, 1), 5: (16, 0), 6: (32, 0)},
+    "Ne=3,4 thread, 5,6 lane in 32-thread CTAs": {3: (1, 1), 4: (1, 1), 5: (16, 0, 32), 6: (32, 0, 32)},
+    "Ne=3,4 thread, 5,6 lane in 64-thread CTAs": {3: (1, 1), 4: (1, 1), 5: (16, 0, 64), 6: (32, 0, 64)},
+    "Ne=3 thread, 4,5,6 lane in 32-thread CTAs": {3: (1, 1), 4: (16, 0, 32), 5: (16, 0, 32), 6: (32, 0, 32)},
     "all thread": {3: (1, 1), 4: (1, 1), 5: (1, 1), 6: (1, 1)},
 }
 only = sys.argv[1:]
