@@ -542,6 +542,8 @@ extern "C" int phf_am_single_run(const phf_am_config *cfg, int64_t n_chains, dou
     if (block % 32 != 0 || block > 128)
         return set_error(PHF_EINVAL, "cfg.block_threads must be a multiple of 32, at most 128");
     if (cfg->stage_groups < 0) return set_error(PHF_EINVAL, "cfg.stage_groups must be >= 0");
+    if (depth > 1 && (uint64_t)cfg->t0 + cfg->n_iters > 0xFFFFFF00ull)  // (the ring prepares up to 64 iterations ahead)
+        return set_error(PHF_EINVAL, "iteration counter overflow (speculative form)");
     if (depth > 1)
         return am_single_spec_launch(*cfg, lanes, depth, n_chains, block, state, dataset_id, temperature, datasets, groups,
                                      samples, (cudaStream_t)stream);
