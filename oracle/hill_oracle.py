@@ -393,3 +393,69 @@ def construct_posterior_predictive_cdfs(alphas, betas, mus, ss):
         pic50_pdf_sum += st.logistic.pdf(pic50_x_range, mus[i], ss[i])
     return (hill_x_range, hill_cdf_sum / num_iterations, pic50_x_range, pic50_cdf_sum / num_iterations,
             hill_pdf_sum / num_iterations, pic50_pdf_sum / num_iterations)
+
+
+# ----------------------------------------------------------------------------
+# Speculative (prefetching) evaluation of the same loop -- an executable statement of the round protocol of
+# pyhillfit_b200/csrc/phf_single_spec.cu, used by tests/test_oracle_golden.py to show that it commits exactly the
+# sequential chain: S proposals per round, proposal g made from the state "the g iterations before it were rejected"
+# (theta and the log-target unchanged, mean / covariance / loga adapted with accepted = 0), the first accepted one ends
+# the round, the state after k-1 rejections is hypothesis k-1 itself.
+# ----------------------------------------------------------------------------
+def adaptive_metropolis_speculative(target, theta0, iterations, thinning, variant, depth, seed=1, chain_id=0):
+    """Philox stream only.  Returns (chain, acceptance, rounds) -- chain and acceptance equal to
+    adaptive_metropolis(..., rng="philox") bit for bit; `rounds` is how many rounds the iterations took."""
+    theta = np.array(theta0, dtype=float)
+    d = len(theta)
+    cov, adapt_when, reset_mean = am_defaults(variant, theta)
+    dg = np.diag(cov).copy()
+    cov[np.diag_indices(d)] = np.where(dg > 0, dg, COV0_DIAG_FLOOR)
+    mean = np.copy(theta)
+    lt = target(theta)
+    chain = np.zeros((iterations // thinning + 1, d + 1))
+    chain[0, :] = np.concatenate((theta, [lt]))
+    loga = 0.
+    n_acc = 0
+    t = 0          # iterations completed
+    rounds = 0
+
+    def adapt(mean, cov, loga, th, ti, accepted):
+        # the adaptation after iteration ti (PyHillFit.py:840-846, PyHillTemp.py:114-122), th already post-accept
+        if reset_mean and ti == adapt_when:
+            mean = np.copy(th)
+        if ti > adapt_when:
+            gamma_s = 1. / ((ti - adapt_when) + 1.) ** 0.6
+            bit = np.array([th - mean])
+            cov = (1 - gamma_s) * cov + gamma_s * np.dot(np.transpose(bit), bit)
+            mean = (1 - gamma_s) * mean + gamma_s * th
+            loga = loga + gamma_s * (accepted - 0.25)
+        return mean, cov, loga
+
+    while t < iterations:
+        rounds += 1
+        n_valid = min(depth, iterations - t)
+        hyp, props = [], []
+        h_mean, h_cov, h_loga = mean, cov, loga
+        for g in range(n_valid):                      # hypothesis g: iterations t+1 .. t+g rejected
+            if g > 0:
+                h_mean, h_cov, h_loga = adapt(h_mean, h_cov, h_loga, theta, t + g, 0)
+            u, z = philox_draw(seed, chain_id, t + 1 + g, d)
+            star = theta + math.exp(0.5 * h_loga) * (guarded_cholesky(h_cov) @ z)
+            hyp.append((h_mean, h_cov, h_loga))
+            props.append((u, star, target(star)))     # (every group evaluates its target in parallel on the device)
+        first = next((g for g in range(n_valid) if np.log(props[g][0]) < props[g][2] - lt), None)
+        k = n_valid if first is None else first + 1
+        for j in range(1, k):                         # rows that fall on the rejected iterations: state unchanged
+            if (t + j) % thinning == 0:
+                chain[(t + j) // thinning, :] = np.concatenate((theta, [lt]))
+        mean, cov, loga = hyp[k - 1]                  # the state after k-1 rejections IS hypothesis k-1
+        accepted = 0
+        if first is not None:
+            theta, lt = props[first][1], props[first][2]
+            accepted = 1
+            n_acc += 1
+        mean, cov, loga = adapt(mean, cov, loga, theta, t + k, accepted)
+        if (t + k) % thinning == 0:
+            chain[(t + k) // thinning, :] = np.concatenate((theta, [lt]))
+        t += k
+    return chain, n_acc / float(iterations), rounds

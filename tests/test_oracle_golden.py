@@ -249,3 +249,38 @@ def test_am_zero_start_component_freezes_that_coordinate(table):
     npr.seed(25)
     chain_np, _ = ho.adaptive_metropolis(target, theta0, 400, 5, "fit", rng="numpy")
     assert np.all(np.abs(chain_np[:, 1]) < 1e-12) and np.ptp(chain_np[:, 0]) > 1e-3
+
+
+@pytest.mark.parametrize("variant,model,depth", [("temp", 2, 4), ("fit", 2, 2), ("fit", 1, 8), ("temp", 1, 3)])
+def test_speculative_round_protocol_commits_the_sequential_chain(table, variant, model, depth):
+    """The round protocol of csrc/phf_single_spec.cu, stated in numpy (hill_oracle.adaptive_metropolis_speculative):
+    S proposals per round under the hypothesis that their predecessors are rejected, the first accepted one ends the
+    round.  It reproduces the sequential loop BIT FOR BIT (chain rows incl. the thinned ones that fall on rejected
+    iterations, acceptance), across the start of adaptation and PyHillTemp's mean reset, and needs ~(1 - 0.75^S)/0.25
+    times fewer rounds than iterations once the acceptance rate has settled near 0.25."""
+    concs, y = table.concat("Amiodarone", "hERG")
+    w0, w100, wo = ho.masks(y)
+    pb = ho.compute_pi_bit_of_log_likelihood(wo)
+    theta0 = np.ones(3 if model == 2 else 2) if variant == "temp" else (np.array([6.0, 0.9, 7.0]) if model == 2
+                                                                         else np.array([6.0, 7.0]))
+    temp = 0.421875 if variant == "temp" else 1
+
+    def target(th):
+        with np.errstate(all="ignore"):
+            return ho.log_target(model, y, w0, w100, wo, concs, th, temp, pb)
+
+    cov0, _, reset = ho.am_defaults(variant, theta0)
+    orig = ho.am_defaults
+    ho.am_defaults = lambda v, t0: (cov0.copy(), 60, reset)      # adaptation (and the mean reset) inside the run
+    try:
+        iters, thin = 613, 5                                       # not a multiple of the depth or the thinning
+        want, acc = ho.adaptive_metropolis(target, theta0, iters, thin, variant, rng="philox", seed=9, chain_id=3)
+        got, acc_s, rounds = ho.adaptive_metropolis_speculative(target, theta0, iters, thin, variant, depth, seed=9,
+                                                                chain_id=3)
+    finally:
+        ho.am_defaults = orig
+    assert np.array_equal(got, want)
+    assert acc_s == pytest.approx(acc, abs=1e-12)   # (a count / n here, a running mean in the sequential loop)
+    a = max(acc, 1e-3)
+    expect = iters * a / (1 - (1 - a) ** depth)                    # rounds if every iteration accepted with probability a
+    assert iters / depth <= rounds <= min(iters, 1.35 * expect + 10)
