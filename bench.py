@@ -699,23 +699,28 @@ def config3(cx):
     for ip, (dg, ch) in enumerate(pairs):
         by_ne.setdefault(len(table.experiments(dg, ch)), []).append(ip)
     K3 = 1000
-    hier, tot_n, tot_flops, forms = [], 0, 0.0, {}
+    hier, tot_n, tot_flops = [], 0, 0.0
+    n_all = 256 * len(pairs)
     for ne, idxs in sorted(by_ne.items()):
         exs = [table.experiments(*pairs[i]) for i in idxs]
         hp = HierPack(exs)
         hid = np.repeat(np.arange(len(idxs), dtype=np.int32), 256)
         th0 = np.tile(np.concatenate(([1.0, 4.0, 6.0, 0.3], np.tile([5.5, 1.0], ne), [8.0])), (len(hid), 1))
-        hs = HierarchicalSampler(hp, hid, th0, pr, seed=ne, thinning=5, device=dev)
+        hs = HierarchicalSampler(hp, hid, th0, pr, seed=ne, thinning=5, device=dev, co_resident_chains=n_all - len(hid))
         hb = torch.empty((hs.n, K3 // 5, hs.d + 1), dtype=torch.float64, device=dev)
         hier.append((hs, hb, torch.cuda.Stream(device=dev)))
         tot_n += hs.n
         tot_flops += 256.0 * sum(hier_flops_per_iteration(ne, sum(len(e) for e in ex)) for ex in exs)
+    from pyhillfit_b200 import _lib as _l
+    _lib_hier_lanes = _l.load().phf_am_hier_lanes
     per_ne = {}
     serial_t = 0.0
     for hs, hb, _ in hier:
         t = _timed(torch, lambda hs=hs, hb=hb: hs.run(K3, samples=hb))
         serial_t += t
-        per_ne["Ne=%d" % hs.n_expts] = {"chains": hs.n, "value_alone": hs.n * K3 / t}
+        with torch.cuda.device(dev):
+            form = hs.lanes or int(_lib_hier_lanes(hs.n_expts, hs.n))
+        per_ne["Ne=%d" % hs.n_expts] = {"chains": hs.n, "value_alone": hs.n * K3 / t, "lanes_per_chain": form}
 
     def all_at_once():   # the four launches are independent: one stream each, the small ones fill the big one's gaps
         ev = torch.cuda.Event()
@@ -774,7 +779,8 @@ def config3(cx):
     out["config3_hierarchical"] = {"chains": tot_n, "iters": K3, "value": tot_n * K3 / tot_t, "unit": UNIT,
                                    "value_back_to_back": tot_n * K3 / serial_t, "e2e": e2e3, "per_n_expts": per_ne,
                                    "flops_per_chain_iteration": tot_flops / tot_n,
-                                   "note": "dim 11..17, four launches (Ne = 3, 4, 5, 6) on four streams"}
+                                   "note": "dim 11..17, four launches (Ne = 3, 4, 5, 6) on four streams; lanes_per_chain: 1 = one "
+                                           "thread per chain, 4 = four lanes per chain, 16 / 32 = one lane per parameter"}
     return out
 
 

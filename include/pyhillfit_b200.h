@@ -102,8 +102,9 @@ typedef struct phf_am_config {
     int32_t stage_groups;        /* shared-memory staging capacity per CTA in dose groups / points (0: read via L1) */
     int32_t block_threads;       /* 0: library default (threads per CTA, multiple of 32, <= 128) */
     int32_t lanes_per_chain;     /* single-level: 1, 2 or 4 lanes cooperate on one chain; 0: chosen from n_chains
-                                    (phf_am_single_lanes).  Hierarchical: 16 / 32 = one lane per parameter row, 1 = one
-                                    thread per chain (n_expts <= 6), 0: chosen from n_expts and n_chains.  Results of
+                                    (phf_am_single_lanes).  Hierarchical: 16 / 32 = one lane per parameter row, 4 = four
+                                    lanes per chain (n_expts <= 5), 1 = one thread per chain (n_expts <= 6), 0: chosen
+                                    from n_expts and n_chains.  Results of
                                     different lane counts agree to rounding (the reduction order differs), not bit
                                     for bit. */
     int32_t min_ctas_hint;       /* single-level only, 0: library default (3).  Register budget of the kernel variant,
@@ -204,16 +205,21 @@ int phf_hier_log_target_batch(int64_t n, const double *theta, int32_t theta_stri
                               const phf_hier_priors *priors /* HOST pointer */, double *log_target, void *stream);
 
 /* All chains of one call share n_expts (so dim); state rows are PHF_STATE_SIZE(dim) doubles.
- * n_expts <= PHF_HIER_MAX_EXPTS: lane-per-parameter kernels (16 or 32 lanes per chain: the latency form), or, with
- * cfg->lanes_per_chain = 1 and n_expts <= 6, one thread per chain (the throughput form: twice the rate of the lane
- * kernel for tens of thousands of chains; cfg->lanes_per_chain = 0 picks it for n_expts <= 4 and >= 64 chains per
- * SM); up to PHF_HIER_BIG_MAX_EXPTS: warp-per-chain kernel (takes a stream-ordered temporary of
+ * n_expts <= PHF_HIER_MAX_EXPTS: lane-per-parameter kernels (16 or 32 lanes per chain: the latency form); with
+ * cfg->lanes_per_chain = 4 and n_expts <= 5, four lanes per chain that split data points, draws and the rows of the
+ * factorisation (the mid-size form); with cfg->lanes_per_chain = 1 and n_expts <= 6, one thread per chain (the
+ * throughput form).  cfg->lanes_per_chain = 0 picks the lane kernels below 32 chains per SM, four lanes from there on
+ * (n_expts <= 5) and one thread per chain for n_expts <= 3 from 160 chains per SM; up to PHF_HIER_BIG_MAX_EXPTS: warp-per-chain kernel (takes a stream-ordered temporary of
  * n_chains * dim (dim+1) / 2 doubles for the Cholesky factors).  The kernels run the same algorithm on the same
  * Philox stream and agree to rounding (the log-target's summation order differs).
  * phf_am_hier_init also VALIDATES the packed data the run calls will trust: every chain's dataset must have exactly
  * n_expts experiments and every point of it an experiment index in [0, n_expts) (the kernels use that index as a
  * shuffle lane / shared-memory index); otherwise PHF_EINVAL.  The check reads a flag back, so init synchronises
  * `stream`; phf_am_hier_run is asynchronous and trusts a pack that init accepted. */
+/* lanes per chain phf_am_hier_run picks for `n_chains` concurrently running chains of `n_expts` experiments when
+ * cfg->lanes_per_chain == 0: 16 / 32 (lane kernels), 4, or 1 (current device) */
+int phf_am_hier_lanes(int32_t n_expts, int64_t n_chains);
+
 int phf_am_hier_init(int32_t n_expts, int64_t n_chains, const double *theta0 /* [n,dim] */,
                      const double *cov0_tri /* [n, dim(dim+1)/2] */, const int32_t *dataset_id,
                      const phf_hier_dataset *datasets, const phf_hier_point *points,

@@ -438,18 +438,30 @@ static int launch_am_hier(const phf_am_config &cfg, int64_t n, double *state, co
 
 // phf_hier_thread.cu: one thread per chain, n_expts <= kHierThreadMaxExpts
 constexpr int kHierThreadMaxExpts = 6;
-// cfg.lanes_per_chain == 0 picks the thread kernel for at most 4 experiments once the launch has 64 chains per SM:
-// measured on B200 (scripts/hier_probe.py, ms per 1000 iterations, lane kernel vs thread kernel): Ne = 3, 9 856 chains
-// 11.3 vs 11.4, 19 712: 20.0 vs 14.4, 39 424: 38.8 vs 16.0; Ne = 4, 10 496 chains: 12.0 vs 12.2 alone -- a tie -- but
-// next to the Ne = 3 launch (BASELINE config 3 runs its four launches on four streams) the thread form's 328 warps fit
-// beside the Ne = 3 CTAs where the lane form's 5 248 warps queue behind them: 30.8 against 33.5 ms for the whole
-// configuration (scripts/config3_probe.py, profiles/r02_config3_probe.txt).  Five and six experiments (3 072 and 768
-// chains) stay with the lane kernel: 5.0 / 4.0 ms against 14.9 / 15.0 (a lone warp's iteration is ~25 000 cycles).
-constexpr int kHierThreadAutoMaxExpts = 4;
-constexpr int kHierThreadMinChainsPerSm = 64;
+// cfg.lanes_per_chain == 0: which of the three forms runs a launch of n chains.  Measured on B200 (scripts/hier_probe.py,
+// profiles/r02_hier_forms_by_size.txt; ms per 1000 iterations, lane / thread / quad kernel):
+//   Ne = 3:  2 464 chains 3.8 / 10.1 / 4.8;  4 928: 6.9 / 10.2 / 5.7;  9 856: 11.1 / 10.3 / 6.5;  19 712: 19.5 / 12.6 / 11.9;
+//           24 640: 23.8 / 12.8 / 13.4;  39 424: 37.6 / 16.0 / 19.6
+//   Ne = 4:  2 624: 4.1 / 10.2 / 5.4;  5 248: 7.3 / 10.3 / 6.5;  10 496: 12.1 / 11.1 / 8.2;  41 984: 47.7 / 28.6 / 24.2
+//   Ne = 5:  3 072: 5.1 / 13.4 / 6.9;  6 144: 9.3 / 13.4 / 7.9;  12 288: 17.4 / 13.9 / 9.9;  24 576: 32.5 / 24.1 / 19.3
+// -> the lane kernel (16 / 32 lanes per chain: the shortest iteration) below 32 chains per SM; four lanes per chain from
+// there on; one thread per chain (the fewest instructions per chain-iteration, but it needs two to three warps per
+// sub-partition to hide its serial stream) only where its Cholesky factor fits in registers (Ne <= 3) and the launch
+// has 160 chains per SM.  With 4 and 5 experiments the thread form is held to 4 warps per SM by its 50-60 KB of shared
+// memory per warp and never catches the four-lane form.  Six experiments and more: lane kernel (dim 17 does not fit
+// the four-lane form's register budget).
+constexpr int kHierQuadMinChainsPerSm = 32;
+constexpr int kHierThreadAutoMaxExpts = 3;
+constexpr int kHierThreadMinChainsPerSm = 160;
 int am_hier_thread_launch(const phf_am_config &cfg, int32_t n_expts, int64_t n, double *state, const int32_t *dataset_id,
                           const phf_hier_dataset *datasets, const phf_hier_point *points, const phf_hier_priors &pr,
                           double *samples, cudaStream_t s);
+
+// phf_hier_quad.cu: four lanes per chain, n_expts <= kHierQuadMaxExpts
+constexpr int kHierQuadMaxExpts = 5;
+int am_hier_quad_launch(const phf_am_config &cfg, int32_t n_expts, int64_t n, double *state, const int32_t *dataset_id,
+                        const phf_hier_dataset *datasets, const phf_hier_point *points, const phf_hier_priors &pr,
+                        double *samples, cudaStream_t s);
 
 // phf_hier_big.cu
 int hier_big_target_launch(int64_t n, const double *theta, int32_t theta_stride, const double *cov0,
@@ -512,6 +524,16 @@ extern "C" int phf_am_hier_init(int32_t n_expts, int64_t n_chains, const double 
     return check_launch("am_hier_init_kernel");
 }
 
+extern "C" int phf_am_hier_lanes(int32_t n_expts, int64_t n_chains)
+{
+    if (n_expts < 1 || n_expts > PHF_HIER_BIG_MAX_EXPTS) return set_error(PHF_ENOTSUP, "n_expts outside 1..128");
+    if (n_expts > PHF_HIER_MAX_EXPTS) return 32;  // one warp per chain (phf_hier_big.cu)
+    const int64_t sms = sm_count();
+    if (n_expts <= kHierThreadAutoMaxExpts && n_chains >= sms * kHierThreadMinChainsPerSm) return 1;
+    if (n_expts <= kHierQuadMaxExpts && n_chains >= sms * kHierQuadMinChainsPerSm) return 4;
+    return n_expts <= 5 ? 16 : 32;
+}
+
 extern "C" int phf_am_hier_run(const phf_am_config *cfg, int32_t n_expts, int64_t n_chains, double *state,
                                const int32_t *dataset_id, const phf_hier_dataset *datasets,
                                const phf_hier_point *points, const phf_hier_priors *priors, double *samples,
@@ -533,12 +555,16 @@ extern "C" int phf_am_hier_run(const phf_am_config *cfg, int32_t n_expts, int64_
         return am_hier_big_launch(*cfg, n_expts, n_chains, state, dataset_id, datasets, points, *priors, samples, s);
     // cfg.lanes_per_chain: 1 = one thread per chain (throughput form, n_expts <= 6), 16 / 32 = one lane per
     // parameter row (latency form), 0 = chosen from the chain count (see kHierThreadMinChainsPerSm)
-    if (cfg->lanes_per_chain != 0 && cfg->lanes_per_chain != 1 && cfg->lanes_per_chain != 16 && cfg->lanes_per_chain != 32)
-        return set_error(PHF_EINVAL, "phf_am_hier_run: cfg.lanes_per_chain must be 0 (auto), 1, 16 or 32");
-    const bool thread_form = cfg->lanes_per_chain == 1 ||
-                             (cfg->lanes_per_chain == 0 && n_expts <= kHierThreadAutoMaxExpts &&
-                              n_chains >= (int64_t)sm_count() * kHierThreadMinChainsPerSm);
-    if (thread_form) {
+    if (cfg->lanes_per_chain != 0 && cfg->lanes_per_chain != 1 && cfg->lanes_per_chain != 4 && cfg->lanes_per_chain != 16 &&
+        cfg->lanes_per_chain != 32)
+        return set_error(PHF_EINVAL, "phf_am_hier_run: cfg.lanes_per_chain must be 0 (auto), 1, 4, 16 or 32");
+    const int lanes = cfg->lanes_per_chain != 0 ? cfg->lanes_per_chain : phf_am_hier_lanes(n_expts, n_chains);
+    if (lanes == 4) {
+        if (n_expts > kHierQuadMaxExpts)
+            return set_error(PHF_ENOTSUP, "phf_am_hier_run: four lanes per chain need n_expts <= 5");
+        return am_hier_quad_launch(*cfg, n_expts, n_chains, state, dataset_id, datasets, points, *priors, samples, s);
+    }
+    if (lanes == 1) {
         if (n_expts > kHierThreadMaxExpts)
             return set_error(PHF_ENOTSUP, "phf_am_hier_run: one thread per chain needs n_expts <= 6");
         return am_hier_thread_launch(*cfg, n_expts, n_chains, state, dataset_id, datasets, points, *priors, samples, s);

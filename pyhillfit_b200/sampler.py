@@ -214,12 +214,15 @@ class HierarchicalSampler(_Base):
     """n independent chains of the hierarchical model; every chain's dataset has `n_expts` experiments."""
 
     def __init__(self, pack, dataset_id, theta0, priors, cov0=None, adapt_when=None, seed=1, chain_id_base=0,
-                 thinning=5, device=None, lanes=0, block_threads=0):
-        """lanes: 1 = one thread per chain (throughput form, at most 6 experiments), 16 / 32 = one lane per parameter
-        row (latency form), 0 = the library picks from the chain count."""
+                 thinning=5, device=None, lanes=0, block_threads=0, co_resident_chains=0):
+        """lanes: 1 = one thread per chain (at most 6 experiments), 4 = four lanes per chain splitting points, draws and
+        the rows of the factorisation (at most 5 experiments), 16 / 32 = one lane per parameter row (latency form),
+        0 = the library picks from the chain count (phf_am_hier_lanes) -- `co_resident_chains`: chains of OTHER samplers
+        whose launches run concurrently with this one (other streams); a launch that is small by itself but shares the GPU
+        takes the four-lane form instead of the 16-lane one (a quarter of the warps queueing for SMs)."""
         assert isinstance(pack, HierPack)
-        if lanes not in (0, 1, 16, 32):
-            raise ValueError("lanes must be 0, 1, 16 or 32")
+        if lanes not in (0, 1, 4, 16, 32):
+            raise ValueError("lanes must be 0, 1, 4, 16 or 32")
         self.lanes = int(lanes)
         theta0 = np.atleast_2d(np.asarray(theta0, dtype=np.float64))
         n, dim = theta0.shape
@@ -240,6 +243,11 @@ class HierarchicalSampler(_Base):
         self.pack, self.priors = pack, priors
         self._alloc_common(n, theta0, cov0, device)
         torch = self.torch
+        if self.lanes == 0 and co_resident_chains > 0 and self.n_expts <= 5:
+            with torch.cuda.device(self.device):
+                own = int(_lib.load().phf_am_hier_lanes(self.n_expts, n))
+                if own in (16, 32) and int(_lib.load().phf_am_hier_lanes(self.n_expts, n + int(co_resident_chains))) in (1, 4):
+                    self.lanes = 4
         self.dataset_id = torch.from_numpy(ids).to(self.device)
         self.ds_dev, self.pts_dev = pack.device(self.device)
         with torch.cuda.device(self.device):

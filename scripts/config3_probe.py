@@ -48,6 +48,10 @@ def timed(fn, reps=3):
 choices = {
     "round-1 default (Ne=3 thread/smem, others lane)": {3: (1, 1), 4: (16, 0), 5: (16, 0), 6: (32, 0)},
     "Ne=3,4 thread, 5,6 lane": {3: (1, 1), 4: (1, 1), 5: (16, 0), 6: (32, 0)},
+    "Ne=3 thread, 4 quad, 5,6 lane": {3: (1, 1), 4: (4, 0), 5: (16, 0), 6: (32, 0)},
+    "Ne=3 thread, 4,5 quad, 6 lane": {3: (1, 1), 4: (4, 0), 5: (4, 0), 6: (32, 0)},
+    "Ne=3,4,5 quad, 6 lane": {3: (4, 0), 4: (4, 0), 5: (4, 0), 6: (32, 0)},
+    "library's choice": {3: (0, 0), 4: (0, 0), 5: (0, 0), 6: (0, 0)},
     "Ne=3,4 thread, 5,6 lane in 32-thread CTAs": {3: (1, 1), 4: (1, 1), 5: (16, 0, 32), 6: (32, 0, 32)},
     "Ne=3,4 thread, 5,6 lane in 64-thread CTAs": {3: (1, 1), 4: (1, 1), 5: (16, 0, 64), 6: (32, 0, 64)},
     "Ne=3 thread, 4,5,6 lane in 32-thread CTAs": {3: (1, 1), 4: (16, 0, 32), 5: (16, 0, 32), 6: (32, 0, 32)},

@@ -19,7 +19,7 @@ print("Ne %d (%d pairs): chains, lanes, ms per %d iterations, chain-it/s, accept
 for per in pers:
     ids = np.repeat(np.arange(len(pairs), dtype=np.int32), per)
     th0 = np.tile(np.concatenate(([1.0, 4.0, 6.0, 0.3], np.tile([5.5, 1.0], ne), [8.0])), (len(ids), 1))
-    for lanes in (16 if ne <= 5 else 32, 1):
+    for lanes in ((16 if ne <= 5 else 32, 1, 4) if ne <= 5 else (32, 1)):
         s = HierarchicalSampler(pack, ids, th0, pr, seed=ne, thinning=5, adapt_when=100, lanes=lanes)
         buf = torch.empty((s.n, K // 5, s.d + 1), dtype=torch.float64, device="cuda")
         s.run(K, samples=buf); torch.cuda.synchronize()

@@ -19,9 +19,10 @@ def table():
 
 
 @pytest.mark.parametrize("drug,channel,lanes", [("Amiodarone", "hERG", 0), ("Dofetilide", "hERG", 0),
-                                                ("Amiodarone", "hERG", 1)])
+                                                ("Amiodarone", "hERG", 1), ("Amiodarone", "hERG", 4),
+                                                ("Dofetilide", "hERG", 4)])
 def test_hierarchical_posterior_matches_reference_chain(table, drug, channel, lanes):
-    """(lanes = 0: the lane-per-parameter kernel; 1: the thread-per-chain kernel.)  64 GPU chains vs one reference chain (python/PyHillFit.py:481-511 loop + :173-193 target, numpy RNG, 2e5
+    """(lanes = 0: the lane-per-parameter kernel; 1: the thread-per-chain kernel; 4: four lanes per chain.)  64 GPU chains vs one reference chain (python/PyHillFit.py:481-511 loop + :173-193 target, numpy RNG, 2e5
     iterations): 5/25/50/75/95 % quantiles of all 5+2Ne parameters within 4 Monte-Carlo standard errors of the quantile
     estimates (tests/_stats.py)."""
     from pyhillfit_b200.packing import HierPack

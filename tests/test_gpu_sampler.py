@@ -149,9 +149,10 @@ def test_row_major_samples_are_the_transpose(table, model, lanes):
     assert np.array_equal(a.state.cpu().numpy(), b.state.cpu().numpy())
 
 
-@pytest.mark.parametrize("lanes", [0, 1])
+@pytest.mark.parametrize("lanes", [0, 1, 4])
 def test_hier_trajectories_follow_oracle(table, lanes):
-    """lanes = 0: the lane-per-parameter kernel (few chains); lanes = 1: the thread-per-chain kernel."""
+    """lanes = 0: the lane-per-parameter kernel (few chains); lanes = 1: the thread-per-chain kernel; lanes = 4: four
+    lanes per chain (at most 5 experiments)."""
     from pyhillfit_b200.packing import HierPack
     from pyhillfit_b200.sampler import HierarchicalSampler, hier_priors, variant_defaults
     pr, shapes, scales, locs = hier_priors()
@@ -161,9 +162,11 @@ def test_hier_trajectories_follow_oracle(table, lanes):
         by_ne.setdefault(len(table.experiments(d, c)), []).append(ip)
     assert sorted(by_ne) == [3, 4, 5, 6]
     for ne, idxs in sorted(by_ne.items()):
+        if lanes == 4 and ne > 5:
+            continue
         use = idxs[:3]
         pack = HierPack([table.experiments(*pairs[i]) for i in use])
-        ids = np.repeat(np.arange(len(use), dtype=np.int32), 2)
+        ids = np.repeat(np.arange(len(use), dtype=np.int32), 2 if lanes != 4 else 3)   # 9 chains: a ragged last warp of quads
         dim = 5 + 2 * ne
         rng = np.random.default_rng(ne)
         theta0 = np.concatenate([np.tile([1.0, 4.0, 6.0, 0.3], (len(ids), 1)),
@@ -555,3 +558,38 @@ def test_host_entry_point_concurrent_calls_discarded_burn_in_and_release(table):
     assert L.phf_am_single_run_host(C.byref(cfg), len(ids), st.ctypes.data, ids.ctypes.data, temps.ctypes.data,
                                     pack.n_datasets, pack.datasets.ctypes.data, len(pack.groups),
                                     pack.groups.ctypes.data, buf.ctypes.data, 4, 0) == -1
+
+
+@pytest.mark.parametrize("ne", [3, 4, 5])
+def test_hier_four_lane_kernel_segments_layouts_and_ragged_counts(table, ne):
+    """The four-lanes-per-chain hierarchical kernel (csrc/phf_hier_quad.cu): launches are resumable bit for bit at
+    boundaries off the thinning grid, the row-major layout is the transpose, a chain count that fills neither a warp of
+    quads nor a CTA changes nothing for the chains that are there, and the library picks this form for mid-size
+    launches."""
+    from pyhillfit_b200 import _lib
+    from pyhillfit_b200.packing import HierPack
+    from pyhillfit_b200.sampler import HierarchicalSampler, hier_priors
+    pr, shapes, scales, locs = hier_priors()
+    pairs = [p for p in table.pairs() if len(table.experiments(*p)) == ne][:4]
+    pack = HierPack([table.experiments(*p) for p in pairs])
+    ids = np.repeat(np.arange(len(pairs), dtype=np.int32), 11)[:-3]            # 41 chains
+    rng = np.random.default_rng(ne)
+    theta0 = np.concatenate([np.tile([1.0, 4.0, 6.0, 0.3], (len(ids), 1)),
+                             np.tile([5.0, 1.0], (len(ids), ne)) + rng.uniform(-0.3, 0.3, (len(ids), 2 * ne)),
+                             np.full((len(ids), 1), 8.0)], axis=1)
+    kw = dict(adapt_when=50, seed=5, chain_id_base=77, thinning=5, lanes=4)
+    a = HierarchicalSampler(pack, ids, theta0, pr, **kw)
+    whole = a.run(400).cpu().numpy()
+    b = HierarchicalSampler(pack, ids, theta0, pr, block_threads=64, **kw)
+    parts = [b.run(k, row_major=True).cpu().numpy().transpose(1, 0, 2) for k in (7, 131, 262)]
+    assert np.array_equal(whole, np.concatenate(parts, axis=1))
+    assert np.array_equal(a.state.cpu().numpy(), b.state.cpu().numpy())
+    c = HierarchicalSampler(pack, ids[:17], theta0[:17], pr, **kw)              # the same chains in a smaller launch
+    assert np.array_equal(c.run(400).cpu().numpy(), whole[:17])
+    assert 0.05 < a.acceptance().mean() < 0.6 and np.all(np.isfinite(whole))
+    L = _lib.load()
+    sms = 148
+    assert L.phf_am_hier_lanes(ne, 8 * sms) in (16, 32)
+    assert L.phf_am_hier_lanes(ne, 64 * sms) == 4
+    assert L.phf_am_hier_lanes(ne, 300 * sms) == (1 if ne <= 3 else 4)
+    assert L.phf_am_hier_lanes(6, 300 * sms) == 32 and L.phf_am_hier_lanes(50, 10) == 32
