@@ -5,8 +5,9 @@
 // it behind: the kernel issues 42 % of its slots and waits 1.8 cycles per instruction on dependent FP64 latency.  The
 // lane-per-parameter kernel (phf_hier.cu) spreads a chain over 16 lanes, most of which idle through the factorisation.
 // This kernel sits between them: the four lanes q = 0..3 of a chain SPLIT every part of the iteration, so a lane's
-// stream is ~3.2 x shorter than the thread kernel's at ~1.25 x its total work, and four times as many warps are there
-// to overlap:
+// stream is 2.3 x shorter than the thread kernel's (2 836 against 6 542 instructions at four experiments) at 1.7 x its
+// total work, and four times as many warps are there to overlap -- the form for mid-size launches (measured
+// crossovers: phf_hier.cu, phf_am_hier_lanes):
 //   * draws:      lane q makes Philox call q (+ 4): one call, at most two Box-Muller pairs per lane instead of 4 + 6;
 //   * rows:       lane q owns rows i = q, q+4, q+8, ... of the covariance (private shared-memory columns), of the
 //                 Cholesky factor (registers) and of theta / mean (registers);
