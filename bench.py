@@ -640,7 +640,8 @@ def strong_configs(cx):
         out[tag] = {"scaling": "strong", "chains": chains, "chains_per_gpu_rank0": res["chains_local"], "iters": iters,
                     "value": chains * iters / sec, "unit": UNIT, "seconds": sec, "wall_seconds": cx.max_over_ranks(wall),
                     "phase_seconds": {"sampling_max_over_ranks": sample_s, "all_gather_and_trapezium": gather_s},
-                    "lanes_rank0": res["lanes"], "flops_per_chain_iteration": float(flops),
+                    "lanes_rank0": res["lanes"], "speculation_rank0": res["speculation"],
+                    "flops_per_chain_iteration": float(flops),
                     "ln_B12": {"mean_over_pairs": float(lb.mean()), "min": float(lb.min()), "max": float(lb.max()),
                                "Amiodarone_hERG": float(lb[0])},
                     "rank_count_independence": {"lanes": 2, "iterations": 20000, "B12_sha256_16": digest,
