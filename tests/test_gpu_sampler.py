@@ -445,8 +445,9 @@ def test_speculative_evaluation_gives_the_same_chain_bit_for_bit(table, model, v
     depth or the thinning, discarded burn-in rows and both sample layouts; and the chain follows the C oracle."""
     from pyhillfit_b200.packing import SinglePack
     from pyhillfit_b200.sampler import SingleLevelSampler, variant_defaults
-    pairs = [("Amiodarone", "hERG"), ("Bepridil", "hERG"), ("Amitriptyline", "Kv4.3"), ("Dofetilide", "hERG"),
-             ("Diltiazem", "Cav1.2")]
+    pairs = [("Amiodarone", "hERG"), ("Bepridil", "hERG"), ("Amitriptyline", "Kv4.3"),
+             ("Dofetilide", "hERG"),      # five unique doses: the general loop behind the prepared records
+             ("Rufinamide", "hERG")]      # two unique doses: absent (all-zero) prepared records
     pack = SinglePack([table.concat(d, c) for d, c in pairs])
     d = 2 if model == 1 else 3
     n_per = 7                                     # 35 chains: ragged for every lanes x depth
