@@ -28,6 +28,13 @@
 #include "phf_common.cuh"
 #include "phf_math.cuh"
 
+// which erfcx the point loop uses: the table-driven one (32 degree-7 polynomials, 27 fp64 instructions) or the single
+// degree-22 polynomial (39) -- see phf_fastmath.cuh; a kernel uses one form throughout.  Measured: the table form
+// loses 4-13 % in this kernel (profiles/r02_quad_erfcx_ab.txt), like in the other one-point-per-lane kernels
+#ifndef PHF_QUAD_ERFCX
+#define PHF_QUAD_ERFCX fm::erfcx_nonneg
+#endif
+
 namespace phf {
 
 namespace {
@@ -153,8 +160,8 @@ PHF_DI double hier_quad_log_target(const double *T, const double (&th)[5 + 2 * N
             const double p = hill_response(x);
             const double r = v23.x - p;
             const double ta = (100.0 - p) * inv_s_rt2, tb = p * inv_s_rt2;
-            const double qa = fm::erfcx_nonneg(T, ta) * fm::exp_clamped(T, -ta * ta);
-            const double qb = fm::erfcx_nonneg(T, tb) * fm::exp_clamped(T, -tb * tb);
+            const double qa = PHF_QUAD_ERFCX(T, ta) * fm::exp_clamped(T, -ta * ta);
+            const double qb = PHF_QUAD_ERFCX(T, tb) * fm::exp_clamped(T, -tb * tb);
             const double dphi = 1.0 - 0.5 * (qa + qb);
             const double cb = fma(r * r, inv2s2, safe_log_q(T, dphi)) + sigma_l;
             contrib[u] = has ? cb : 0.0;
