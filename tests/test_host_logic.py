@@ -344,3 +344,33 @@ def test_dataset_cost_orders_datasets_by_work():
     assert c[0] == c[4] and c[1] > c[0] and c[2] > c[1] and c[3] < c[0]
     assert c[1] - c[0] == pytest.approx(133.0) and c[2] - c[0] == pytest.approx(266.0)
     assert np.all(pack.dataset_cost(1) < c)
+
+
+def test_bench_flop_counts_match_the_survey_cost_table():
+    """bench.py's algorithmic-work figures (the roofline's numerator) against SURVEY.md section 8d's worked values:
+    model 2 on Amiodarone/hERG (d = 3, 4 doses, one of them censored) = 954 flops per chain-iteration, model 1 ~ 790,
+    hierarchical Ne = 3, N = 12 ~ 6.1 kflops; a prior-only (t = 0) chain is charged no likelihood."""
+    import importlib.util
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    argv, fd1 = sys.argv, os.dup(1)
+    try:
+        sys.argv = ["bench.py"]
+        spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(root, "bench.py"))
+        bench = importlib.util.module_from_spec(spec)
+        stdout = sys.stdout
+        spec.loader.exec_module(bench)          # (bench.py redirects fd 1 to stderr at import: undone below)
+    finally:
+        sys.argv = argv
+        os.dup2(fd1, 1)
+        os.close(fd1)
+        sys.stdout = stdout
+    from pyhillfit_b200.packing import SinglePack
+    t = Table("crumb_data")
+    pack = SinglePack([t.concat("Amiodarone", "hERG")])
+    g = pack.groups
+    assert bench.flops_per_iteration(2, g) == 954
+    assert 760 <= bench.flops_per_iteration(1, g) <= 820
+    assert bench.flops_per_iteration(2, g, prior_only=True) == 954 - (40 + 58 + 4 * 53 + 3 * 5 + 133 + 6)
+    assert 5900 <= bench.hier_flops_per_iteration(3, 12) <= 6300
+    assert bench.pack_flops(2, pack)[0] == 954
