@@ -6,7 +6,8 @@
 
 Headline workload (BASELINE.json configs[1]): every Crumb (drug, channel) pair (210) x single-level models {1, 2} x 64
 chains = 26 880 chains per GPU, PyHillFit-variant adaptive Metropolis (python/PyHillFit.py:828-856), thinning 5.
-One step = `--iters-per-step` iterations of every chain (two kernel launches, one per model, on two streams),
+One step = `--iters-per-step` iterations of every chain (two kernel launches, one per model, on two streams; inside
+the timed run the two streams are joined with the main stream only before the first and after the last step),
 thinned samples written to HBM.  N > 1: every rank runs the same workload with disjoint Philox chain ids (weak
 scaling, no collective on the data path); the value is chains x iterations over all ranks / max-over-ranks time.
 
@@ -378,16 +379,22 @@ def main():
     main_stream = torch.cuda.current_stream(dev)
     stream_events = None
 
-    def step():
+    def step(first=True, last=True):
+        """one step = one launch per model; the two models' launches go to two streams.  Inside a run of steps the
+        streams are not joined between steps (each stream's launches are ordered among themselves and share nothing
+        with the other stream): `first` makes the streams wait for the main stream, `last` makes the main stream wait
+        for them."""
         if args.serial_models:
             for model in (2, 1):
                 samplers[model].run(K, samples=buffers[model], row_major=row_major)
             return
-        ev = torch.cuda.Event()
-        ev.record(main_stream)
+        if first:
+            ev = torch.cuda.Event()
+            ev.record(main_stream)
         for model in (1, 2):
             st = streams[model]
-            st.wait_event(ev)
+            if first:
+                st.wait_event(ev)
             with torch.cuda.stream(st):
                 if stream_events is not None:   # per-launch duration on the launching stream
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -396,8 +403,9 @@ def main():
                 if stream_events is not None:
                     b.record(st)
                     stream_events[model].append((a, b))
-        for model in (1, 2):
-            main_stream.wait_stream(streams[model])
+        if last:
+            for model in (1, 2):
+                main_stream.wait_stream(streams[model])
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -425,8 +433,8 @@ def main():
     t_begin = time.time()
     stream_events = {1: [], 2: []}
     e0.record(main_stream)
-    for _ in range(args.steps):
-        step()
+    for k in range(args.steps):
+        step(first=k == 0, last=k == args.steps - 1)
     e1.record(main_stream)
     barrier()
     t_end = time.time()
