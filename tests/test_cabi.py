@@ -105,3 +105,31 @@ def test_compute_paths_refuse_to_run_without_cuda():
     pack = SinglePack([(np.array([0.1, 1.0, 10.0]), np.array([5.0, 50.0, 90.0]))])
     with pytest.raises(_lib.PhfError, match="no CPU fallback"):
         SingleLevelSampler(2, pack, np.zeros(1, dtype=np.int32), 1.0, np.ones((1, 3)))
+
+
+def test_launch_shape_selection_without_a_gpu():
+    """phf_am_single_shape / phf_am_hier_lanes only need the SM count (148 is assumed when no device answers): the
+    thresholds behind DESIGN.md sections 3.1b and 3.2c."""
+    from pyhillfit_b200 import _lib
+    L = _lib.load()
+
+    def shape(n, lanes=0, spec=0):
+        lo, so = C.c_int32(-1), C.c_int32(-1)
+        rc = L.phf_am_single_shape(n, lanes, spec, C.byref(lo), C.byref(so))
+        return rc, lo.value, so.value
+
+    assert shape(2152) == (0, 2, 4)          # one GPU's share of the eight-GPU sweep: two lanes x four hypotheses
+    assert shape(4304) == (0, 2, 4)
+    assert shape(8610) == (0, 2, 2)
+    assert shape(17220) == (0, 2, 1)         # the whole sweep on one GPU
+    assert shape(26880) == (0, 2, 1)         # config 2
+    assert shape(4000000) == (0, 1, 1)       # config 5: one thread per chain, no speculation
+    assert shape(2152, spec=1) == (0, 4, 1)  # speculation switched off: the four-lane latency form
+    assert shape(2152, lanes=4) == (0, 4, 4) and shape(4304, lanes=4) == (0, 4, 2)
+    assert shape(100, lanes=1, spec=8)[0] == -1 and shape(100, lanes=3)[0] == -1 and shape(100, spec=3)[0] == -1
+    assert L.phf_am_single_shape(100, 0, 0, None, None) == -1
+    sms = 148
+    assert L.phf_am_hier_lanes(3, 8 * sms) == 16 and L.phf_am_hier_lanes(6, 8 * sms) == 32
+    assert L.phf_am_hier_lanes(3, 40 * sms) == 4 and L.phf_am_hier_lanes(3, 200 * sms) == 1
+    assert L.phf_am_hier_lanes(5, 200 * sms) == 4 and L.phf_am_hier_lanes(6, 200 * sms) == 32
+    assert L.phf_am_hier_lanes(50, 10) == 32 and L.phf_am_hier_lanes(0, 10) == -3
