@@ -288,6 +288,19 @@ int phf_format_e18(double v, char *buf);
 int64_t phf_format_e18_mismatches(const double *data, int64_t n);
 
 /* ------------------------------------------------------------------------------------------------
+ * Least-squares start points.  Replaces the per-pair / per-experiment fit before the sampler,
+ * python/PyHillFit.py:93-102 (objective and sigma0), :699-735 (single-level start), :243-257 (hierarchical start),
+ * for n_datasets datasets in one launch, one thread each: dataset k owns the raw points
+ * concs[offsets[k] .. offsets[k+1]) / responses[...] (uM and % block, every point counts, as in the reference).
+ * The reference minimises with CMA-ES (third-party, absent); this runs the deterministic grid + Nelder-Mead of
+ * pyhillfit_b200/initial_fit.py ("parity unpinned" for the minimiser; the objective is the reference's).
+ * theta: [n_datasets, 2] (pIC50, sigma) for model 1, [n_datasets, 3] (pIC50, Hill, sigma) for model 2; ss: the sum
+ * of squares reached.  All pointers are DEVICE pointers; asynchronous on `stream`.
+ * ---------------------------------------------------------------------------------------------- */
+int phf_best_fit_batch(int model, int64_t n_datasets, const int64_t *offsets, const double *concs,
+                       const double *responses, double pic50_lower, double *theta, double *ss, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Utilities
  * ---------------------------------------------------------------------------------------------- */
 int phf_version(void);

@@ -58,7 +58,7 @@ def run_single_level(dr, args, pairs):
     """python/PyHillFit.py:645-867 for all pairs at once."""
     import torch
     from . import chainio
-    from .initial_fit import best_fit_batch
+    from .initial_fit import best_fit_batch_gpu as best_fit_batch   # phf_best_fit_batch, one thread per dataset
     from .packing import SinglePack
     from .sampler import SingleLevelSampler
     temperature = 1
@@ -140,7 +140,7 @@ def hierarchical_start(experiments, locs, best_fits=None):
     best_fits: the per-experiment fits [Ne, 3] if the caller already made them (all pairs in one batch)."""
     import scipy.stats as st
     from scipy.optimize import minimize
-    from .initial_fit import best_fit_batch
+    from .initial_fit import best_fit_batch_gpu as best_fit_batch   # phf_best_fit_batch, one thread per dataset
     if best_fits is None:
         best_fits, _ = best_fit_batch(2, [(e[:, 0], e[:, 1]) for e in experiments], pic50_lower=-2.0)
     best_fits = np.array(best_fits)
@@ -194,7 +194,7 @@ def run_hierarchical(dr, args, pairs):
         jobs.append(dict(drug=cdrug, channel=cchannel, chain_file=chain_file, experiments=experiments,
                          ne=len(experiments)))
     # per-experiment least-squares fits of every pair in one batch (704 fits for the Crumb table)
-    from .initial_fit import best_fit_batch
+    from .initial_fit import best_fit_batch_gpu as best_fit_batch   # phf_best_fit_batch, one thread per dataset
     all_fits, _ = best_fit_batch(2, [(e[:, 0], e[:, 1]) for j in jobs for e in j["experiments"]], pic50_lower=-2.0)
     at = 0
     for job in jobs:

@@ -49,7 +49,7 @@ assert HIER_POINT_DTYPE.itemsize == 32 and HIER_DATASET_DTYPE.itemsize == 16
 EXPORTS = ["phf_log_target_batch", "phf_am_single_init", "phf_am_single_run", "phf_am_single_lanes",
            "phf_am_single_speculation", "phf_am_single_shape", "phf_am_single_resident_ctas", "phf_hier_log_target_batch",
            "phf_am_hier_lanes", "phf_am_hier_init", "phf_am_hier_run", "phf_am_single_run_host", "phf_am_hier_run_host",
-           "phf_release_workspaces",
+           "phf_release_workspaces", "phf_best_fit_batch",
            "phf_write_rows_text_host",
            "phf_hier_predictive_cdfs", "phf_format_e18", "phf_format_e18_mismatches", "phf_version", "phf_last_error",
            "phf_fp64_peak_probe", "phf_launch_count"]
@@ -95,6 +95,7 @@ def load():
                                            C.c_double, _p, _p]
     L.phf_write_rows_text_host.argtypes = [C.c_char_p, C.c_char_p, _p, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
                                            C.c_int32]
+    L.phf_best_fit_batch.argtypes = [C.c_int, C.c_int64, _p, _p, _p, C.c_double, _p, _p, _p]
     L.phf_format_e18.argtypes = [C.c_double, C.c_char_p]
     L.phf_format_e18_mismatches.argtypes = [_p, C.c_int64]
     L.phf_format_e18_mismatches.restype = C.c_int64

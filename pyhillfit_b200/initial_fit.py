@@ -171,3 +171,38 @@ def best_fit_batch(model, datasets, pic50_lower=PIC50_LOWER):
     hill = np.minimum(hill, 10.0)
     theta = np.stack([pic50, sigma], axis=1) if model == 1 else np.stack([pic50, hill, sigma], axis=1)
     return theta, ss
+
+
+def best_fit_batch_gpu(model, datasets, pic50_lower=PIC50_LOWER, device=None):
+    """best_fit_batch on the device (phf_best_fit_batch, one thread per dataset): same objective, grid, simplex rules,
+    tolerances and fall-backs; `datasets` is a list of (concs, responses) or a tuple (offsets [n+1], concs, responses)
+    of flat arrays.  -> theta0 [n, d], sum of squares [n] as numpy arrays.  Results agree with the host version to
+    the rounding of pow() (tests/test_gpu_fit.py); a million datasets take about a second."""
+    from . import _lib
+    torch = _lib.require_cuda()
+    if isinstance(datasets, tuple) and len(datasets) == 3 and np.ndim(datasets[0]) == 1 and not isinstance(datasets[0], tuple):
+        offsets, concs, resp = (np.ascontiguousarray(a) for a in datasets)
+        offsets = offsets.astype(np.int64)
+    else:
+        if len(datasets) == 0:
+            return np.zeros((0, 2 if model == 1 else 3)), np.zeros(0)
+        lens = np.array([len(c) for c, _ in datasets], dtype=np.int64)
+        offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        concs = np.concatenate([np.asarray(c, dtype=np.float64) for c, _ in datasets])
+        resp = np.concatenate([np.asarray(y, dtype=np.float64) for _, y in datasets])
+    n = len(offsets) - 1
+    if n <= 0:
+        return np.zeros((0, 2 if model == 1 else 3)), np.zeros(0)
+    if offsets[0] != 0 or np.any(np.diff(offsets) <= 0) or offsets[-1] != len(concs) or len(concs) != len(resp):
+        raise ValueError("best_fit_batch_gpu: offsets must start at 0, increase strictly and end at len(concs)")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        d_off = torch.from_numpy(offsets).to(dev)
+        d_c = torch.from_numpy(np.asarray(concs, dtype=np.float64)).to(dev)
+        d_y = torch.from_numpy(np.asarray(resp, dtype=np.float64)).to(dev)
+        theta = torch.empty((n, 2 if model == 1 else 3), dtype=torch.float64, device=dev)
+        ss = torch.empty(n, dtype=torch.float64, device=dev)
+        _lib.check(_lib.load().phf_best_fit_batch(model, n, _lib.ptr(d_off), _lib.ptr(d_c), _lib.ptr(d_y),
+                                                  float(pic50_lower), _lib.ptr(theta), _lib.ptr(ss),
+                                                  _lib.current_stream_ptr()), "phf_best_fit_batch")
+        return theta.cpu().numpy(), ss.cpu().numpy()
