@@ -5,6 +5,8 @@ against the package's own host mirror, so the documented stub is known to work.
     log_target(...)          replaces python/doseresponse.py:187-189 (and :166-184, 203-248 below it)
     run_single_level_loop()  replaces the while-loop at python/PyHillFit.py:828-856 (variant="fit")
                              or python/PyHillTemp.py:87-123 (variant="temp", one chain per temperature)
+    best_fits()              replaces the cma.fmin start point + initial sigma at python/PyHillFit.py:699-735 (and the
+                             per-experiment fits of :243-257 with pic50_lower=-2) for any number of datasets at once
 """
 import ctypes as C
 import os
@@ -67,6 +69,22 @@ def log_target(model, y, where_y_0, where_y_100, where_y_other, concs, params, t
     _check(_phf.phf_log_target_batch(model, C.c_int64(1), _vp(th.data_ptr()), _vp(ids.data_ptr()), _vp(tt.data_ptr()),
                                      _vp(dd.data_ptr()), _vp(gd.data_ptr()), _vp(out.data_ptr()), None, None))
     return out.item()
+
+
+def best_fits(model, datasets, pic50_lower=-3.0):
+    """datasets: list of (concs, responses) -> theta0 [n, d] = (pIC50, [Hill,] sigma0), sum of squares [n]."""
+    import torch
+    offsets = np.concatenate([[0], np.cumsum([len(c) for c, _ in datasets])]).astype(np.int64)
+    dev = lambda a, t: torch.from_numpy(np.ascontiguousarray(a, dtype=t)).cuda()
+    off = dev(offsets, np.int64)
+    cc = dev(np.concatenate([c for c, _ in datasets]), np.float64)
+    yy = dev(np.concatenate([y for _, y in datasets]), np.float64)
+    n, d = len(datasets), 2 if model == 1 else 3
+    th = torch.empty((n, d), dtype=torch.float64).cuda()
+    ss = torch.empty(n, dtype=torch.float64).cuda()
+    _check(_phf.phf_best_fit_batch(model, C.c_int64(n), _vp(off.data_ptr()), _vp(cc.data_ptr()), _vp(yy.data_ptr()),
+                                   C.c_double(pic50_lower), _vp(th.data_ptr()), _vp(ss.data_ptr()), None))
+    return th.cpu().numpy(), ss.cpu().numpy()
 
 
 def run_single_level_loop(model, concs, responses, theta0, cov0, log_target0, loglik_t1_0, temperatures, iterations,

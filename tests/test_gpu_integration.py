@@ -50,3 +50,14 @@ def test_documented_binding_matches_the_host_mirror():
     assert chain.shape == (5, 401, 4)
     assert np.array_equal(chain[:, 0, :], row0)
     assert np.allclose(chain[:, 1:, :], want, rtol=1e-9, atol=1e-9)     # the host call picks its own lane count
+
+
+def test_documented_best_fit_binding_matches_the_package():
+    from pyhillfit_b200.initial_fit import best_fit_batch_gpu
+    rb = _stub()
+    t = Table("crumb_data")
+    data = [t.concat(*p) for p in t.pairs()[:12]]
+    for model in (1, 2):
+        th, ss = rb.best_fits(model, data)
+        wt, ws = best_fit_batch_gpu(model, data)
+        assert np.array_equal(th, wt) and np.array_equal(ss, ws)
