@@ -68,3 +68,24 @@ def test_pyhilltemp_then_compute_bayes_factors_cli(crumb_csv):
     assert compute_bayes_factors.main(["--data-file", crumb_csv, "-d", "0", "-c", "0"]) == 0
     b12 = float(np.loadtxt("BFs/Amiodarone_hERG_B12.txt"))
     assert np.isfinite(b12) and b12 > 0
+
+
+def test_pyhillfit_best_fit_only_cli_all_pairs(crumb_csv):
+    """`PyHillFit -a --best-fit-only` (python/PyHillFit.py:736-746): one best_fit_params.txt per pair from a single
+    phf_best_fit_batch launch, no chain files; the saved fits are the host statement's minima."""
+    import glob
+    from _data import Table
+    from pyhillfit_b200 import PyHillFit
+    from pyhillfit_b200.initial_fit import sum_of_square_diffs, best_fit
+    assert PyHillFit.main(["--data-file", crumb_csv, "-m", "2", "-a", "--best-fit-only"]) == 0
+    files = sorted(glob.glob("output/crumb_data/single-level/*/*/model_2/temperature_1/figures/*_best_fit_params.txt"))
+    assert len(files) == 210
+    assert not glob.glob("output/crumb_data/single-level/*/*/model_2/temperature_1/chain/*.txt")
+    t = Table("crumb_data")
+    for drug, channel in [("Amiodarone", "hERG"), ("Dofetilide", "hERG"), ("Amitriptyline", "Kv4.3")]:
+        got = np.loadtxt("output/crumb_data/single-level/%s/%s/model_2/temperature_1/figures/%s_%s_best_fit_params.txt"
+                         % (drug, channel, drug, channel))
+        concs, y = t.concat(drug, channel)
+        want, ss = best_fit(2, concs, y)
+        assert sum_of_square_diffs((got[0], got[1]), concs, y) == pytest.approx(ss, rel=1e-6)
+        assert got[2] == pytest.approx(want[2], rel=1e-5)
