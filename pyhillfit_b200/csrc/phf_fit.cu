@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(64) best_fit_kernel(int64_t n, const int64_t *
         hill = h0;
         ss = g_ss;
     }
-    double sigma = sqrt(ss / d.n);       // initial_sigma, python/PyHillFit.py:101-102
+    double sigma = d.n > 0 ? sqrt(ss / d.n) : 0.0;  // initial_sigma, python/PyHillFit.py:101-102 (an empty dataset: the floor)
     sigma = fmax(sigma, 2e-3);           // a perfect fit would start at the prior's edge
     hill = fmin(hill, 10.0);
     if (MODEL == 1) {
