@@ -14,11 +14,48 @@ import numpy as np
 def build_parser():
     parser = argparse.ArgumentParser()
     parser.add_argument("-nc", "--num-cores", type=int, help="accepted for compatibility", default=1)
+    # (not in the reference) the fused alternative for every pair of the data file at once: no chain files are read or
+    # written -- pyhillfit_b200.ti.run_ti samples all (pair, model, temperature) chains on the device, accumulates the
+    # temperature-1 log-likelihood in the kernel and integrates; writes the same BFs/<drug>_<channel>_B12.txt files
+    parser.add_argument("--all-fused", action='store_true', default=False,
+                        help="whole thermodynamic-integration sweep for every pair on the device (no chain files)")
+    parser.add_argument("-i", "--iterations", type=int, default=500000, help="--all-fused: iterations per chain")
+    parser.add_argument("-t", "--thinning", type=int, default=5, help="--all-fused: thinning")
+    parser.add_argument("--seed", type=int, default=1, help="--all-fused: Philox seed")
     requiredNamed = parser.add_argument_group('required arguments')
-    requiredNamed.add_argument("-d", "--drug", type=int, help="drug index", required=True)
-    requiredNamed.add_argument("-c", "--channel", type=int, help="channel index", required=True)
+    requiredNamed.add_argument("-d", "--drug", type=int, help="drug index (not needed with --all-fused)")
+    requiredNamed.add_argument("-c", "--channel", type=int, help="channel index (not needed with --all-fused)")
     requiredNamed.add_argument("--data-file", type=str, required=True)
     return parser
+
+
+def run_all_fused(dr, args):
+    """Every (drug, channel) pair of the data file: ti.run_ti over the reference's ladder, then one B12 file per pair
+    (python/compute_bayes_factors.py:83-100).  Under torchrun the sweep is sharded over the ranks; rank 0 writes."""
+    import itertools as it
+    from . import chainio
+    from . import dist as phf_dist
+    from .ti import run_ti
+    jobs, data = [], []
+    for top_drug, top_channel in it.product(dr.drugs, dr.channels):
+        try:
+            num_expts, experiment_numbers, experiments = dr.load_crumb_data(top_drug, top_channel)
+        except Exception:
+            continue
+        concs = np.concatenate([experiments[i][:, 0] for i in range(num_expts)])
+        responses = np.concatenate([experiments[i][:, 1] for i in range(num_expts)])
+        if np.any(np.isnan(responses)):
+            continue
+        drug, channel, chain_file, images_dir = dr.nonhierarchical_chain_file_and_figs_dir(1, top_drug, top_channel, 1)
+        jobs.append((drug, channel))
+        data.append((concs, responses))
+    phf_dist.init_process_group()          # (a no-op for a single process)
+    res = run_ti(data, iterations=args.iterations, thinning=args.thinning, seed=args.seed)
+    if phf_dist.world()[1] == 0:
+        for (drug, channel), Bij in zip(jobs, res["B12"]):
+            chainio.save_bayes_factor(drug, channel, Bij)
+        print("{} Bayes factors written to BFs/".format(len(jobs)))
+    return 0
 
 
 def compute_log_py_approxn(dr, model, pack, chain_file):
@@ -43,6 +80,10 @@ def main(argv=None):
     from . import doseresponse as dr
     from .packing import SinglePack
     dr.setup(args.data_file)
+    if args.all_fused:
+        return run_all_fused(dr, args)
+    if args.drug is None or args.channel is None:
+        parser.error("the following arguments are required: -d/--drug, -c/--channel")
     top_drug, top_channel = dr.drugs[args.drug], dr.channels[args.channel]
     num_expts, experiment_numbers, experiments = dr.load_crumb_data(top_drug, top_channel)
     concs = np.concatenate([experiments[i][:, 0] for i in range(num_expts)])

@@ -89,3 +89,29 @@ def test_pyhillfit_best_fit_only_cli_all_pairs(crumb_csv):
         want, ss = best_fit(2, concs, y)
         assert sum_of_square_diffs((got[0], got[1]), concs, y) == pytest.approx(ss, rel=1e-6)
         assert got[2] == pytest.approx(want[2], rel=1e-5)
+
+
+def test_fused_sweep_for_all_pairs_then_assemble_bfs(crumb_csv, capsys):
+    """The all-pairs story on the device: least-squares fits of both models (PyHillFit -a --best-fit-only), the fused
+    thermodynamic-integration sweep (compute_bayes_factors --all-fused: 17 220 chains, no chain files), then the
+    reference's bookkeeping pass over the files both wrote (assemble_BFs).  The fused B12 of a pair equals
+    ti.run_ti's for the same seed, and agrees with the file-based pipeline's within Monte-Carlo error elsewhere
+    (test_gpu_posterior.py); here: files, formats, counts."""
+    import glob
+    from pyhillfit_b200 import PyHillFit, assemble_BFs, compute_bayes_factors
+    for m in ("1", "2"):
+        assert PyHillFit.main(["--data-file", crumb_csv, "-m", m, "-a", "--best-fit-only"]) == 0
+    assert compute_bayes_factors.main(["--data-file", crumb_csv, "--all-fused", "-i", "20000"]) == 0
+    files = sorted(glob.glob("BFs/*_B12.txt"))
+    assert len(files) == 210
+    b = np.array([float(np.loadtxt(f)) for f in files])
+    assert np.all(np.isfinite(b)) and np.all(b > 0)
+    assert not glob.glob("output/crumb_data/single-level/*/*/model_*/temperature_*/chain/*.txt")
+    capsys.readouterr()
+    assert assemble_BFs.main(["--data-file", crumb_csv]) == 0
+    out = capsys.readouterr().out
+    want = assemble_BFs.summarise(b)
+    assert "NO EVIDENCE: %d" % want["no_evidence"] in out
+    for k in assemble_BFs.BANDS:
+        assert "%s: %d" % (k, want[k]) in out
+    assert sum(want[k] for k in assemble_BFs.BANDS) + want["no_evidence"] == 210

@@ -374,3 +374,45 @@ def test_bench_flop_counts_match_the_survey_cost_table():
     assert bench.flops_per_iteration(2, g, prior_only=True) == 954 - (40 + 58 + 4 * 53 + 3 * 5 + 133 + 6)
     assert 5900 <= bench.hier_flops_per_iteration(3, 12) <= 6300
     assert bench.pack_flops(2, pack)[0] == 954
+
+
+def test_assemble_bfs_bands_and_files(tmp_path, monkeypatch, capsys):
+    """assemble_BFs (python/assemble_BFs.py:55-63, 94-120): the evidence bands at their boundaries, and the command
+    line over BFs/*_B12.txt + best_fit_params.txt files written by this package's own writers."""
+    from pyhillfit_b200 import assemble_BFs, chainio
+    from pyhillfit_b200 import doseresponse as dr
+    band = assemble_BFs.evidence_band
+    assert band(3.0) is None and band(3.0001) == "substantial_b12" and band(10.0) == "substantial_b12"
+    assert band(10.5) == "strong_b12" and band(100.0) == "strong_b12" and band(100.1) == "decisive_b12"
+    assert band(1 / 3.0001) == "substantial_b21" and band(0.05) == "strong_b21" and band(1e-3) == "decisive_b21"
+    assert band(1.0) is None and band(0.0) == "decisive_b21"
+    c = assemble_BFs.summarise([1.0, 0.95, 2.9, 5.0, 50.0, 500.0, 0.2, 0.02, 0.002])
+    assert c == {"substantial_b12": 1, "strong_b12": 1, "decisive_b12": 1, "substantial_b21": 1, "strong_b21": 1,
+                 "decisive_b21": 1, "no_evidence": 3, "ambiguous": 2}
+    z = np.load(os.path.join(GOLD, "datasets.npz"))
+    os.makedirs(tmp_path / "data")
+    f = tmp_path / "data" / "crumb_data.csv"
+    with open(f, "w") as out:
+        out.write("Compound,Channel,Experiment,Dose,Response\n")
+        for row in zip(z["crumb_data__drug"], z["crumb_data__channel"], z["crumb_data__experiment"],
+                       z["crumb_data__dose"], z["crumb_data__response"]):
+            out.write("%s,%s,%d,%r,%r\n" % (row[0], row[1], row[2], float(row[3]), float(row[4])))
+    monkeypatch.chdir(tmp_path)
+    dr.setup(str(f))
+    rng = np.random.default_rng(3)
+    vals = []
+    for top_drug in dr.drugs:
+        for top_channel in dr.channels:
+            b = float(np.exp(rng.normal(0, 3)))
+            vals.append(b)
+            for m in (1, 2):
+                drug, channel, _, images_dir = dr.nonhierarchical_chain_file_and_figs_dir(m, top_drug, top_channel, 1)
+                chainio.save_best_fit_params(images_dir, drug, channel, m, np.arange(1.0, 2.0 + m))
+            chainio.save_bayes_factor(drug, channel, b)
+    assert len(vals) == 210
+    assert assemble_BFs.main(["--data-file", str(f)]) == 0
+    out = capsys.readouterr().out
+    want = assemble_BFs.summarise(vals)
+    assert "NO EVIDENCE: %d" % want["no_evidence"] in out
+    for k in assemble_BFs.BANDS:
+        assert "%s: %d" % (k, want[k]) in out
