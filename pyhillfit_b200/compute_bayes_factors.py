@@ -55,6 +55,10 @@ def run_all_fused(dr, args):
         for (drug, channel), Bij in zip(jobs, res["B12"]):
             chainio.save_bayes_factor(drug, channel, Bij)
         print("{} Bayes factors written to BFs/".format(len(jobs)))
+    import torch.distributed as td
+    if td.is_available() and td.is_initialized():
+        td.barrier()
+        td.destroy_process_group()
     return 0
 
 
